@@ -1,0 +1,202 @@
+/* caar_b200.h — C-ABI of the B200-native compute_and_apply_rhs ("CAAR") library.
+ *
+ * This is the drop-in boundary for the one hot path this repository implements:
+ * HOMME's compute_and_apply_rhs as extracted in E3SM-Project/tinman_sandbox.
+ * Every entry point takes only plain pointers, ints and doubles (no C++ types,
+ * no torch types), so it can be bound from C++, Fortran (bind(C)), ctypes, cgo…
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout,
+ * compute_and_apply_rhs_test/cxx/pointers_only/ = "PO/"):
+ *
+ *   caar_arrays      <- struct Arrays              PO/data_structures.hpp:18-44
+ *   caar_constants   <- struct Constants           PO/data_structures.hpp:46-56
+ *   caar_control     <- struct Control             PO/data_structures.hpp:58-69
+ *   dvv[16]          <- struct Derivative          PO/data_structures.hpp:71-76
+ *   ps0, hyai        <- struct HVCoord             PO/data_structures.hpp:10-16
+ *   caar_run()       <- Homme::compute_and_apply_rhs(TestData&)
+ *                                                  PO/compute_and_apply_rhs.hpp:9
+ *                       (body PO/compute_and_apply_rhs.cpp:15-278, callees
+ *                        preq_hydrostatic :280-312, preq_omega_ps :314-352,
+ *                        gradient/divergence/vorticity_sphere
+ *                        PO/sphere_operators.cpp:9-129)
+ *   caar_norms()     <- print_results_2norm        PO/compute_and_apply_rhs.cpp:372-399
+ *   caar_saxpby_*()  <- saxpby                     saxpby_test/cxx/common.cpp:3-15
+ *
+ * Host array layout is the reference's, bit for bit: row-major
+ * [ie][timelevel][lev][igp][jgp]([comp]) and [ie][igp][jgp][2][2]
+ * (PO/test_macros.hpp:7-54, extents PO/data_structures.cpp:14-31).
+ *
+ * Error convention (the reference has none beyond std::exit/abort): every call
+ * returns CAAR_OK (0) or a CAAR_ERR_* code; caar_last_error() returns a
+ * thread-local, human readable message for the last failing call.
+ * There is NO CPU fallback: without a CUDA device every compute call fails
+ * with CAAR_ERR_CUDA.
+ */
+#ifndef CAAR_B200_H
+#define CAAR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAAR_NP 4 /* GLL points per element edge; compile-time in the reference (config.h.in:1) */
+
+enum {
+  CAAR_OK = 0,
+  CAAR_ERR_INVALID = 1,     /* bad argument (null pointer, bad dims, bad time level …) */
+  CAAR_ERR_CUDA = 2,        /* CUDA runtime/driver error, or no device */
+  CAAR_ERR_NOMEM = 3,       /* device or pinned-host allocation failed */
+  CAAR_ERR_UNSUPPORTED = 4, /* dims the compiled kernels do not cover */
+  CAAR_ERR_STATE = 5        /* call sequence error (e.g. run before set_params) */
+};
+
+/* Kernel selection for caar_run. */
+enum {
+  CAAR_MODE_FAST = 0,   /* fused kernel, register-resident element, parallel warp-shuffle scans,
+                           FMA contraction, shared reciprocals: within 1e-12 of the reference */
+  CAAR_MODE_STRICT = 1  /* reference operation order, no FMA contraction, IEEE divisions,
+                           sequential vertical sums: bit-identical to the reference CPU build */
+};
+
+/* Field bits for caar_upload / caar_download (order = struct Arrays). */
+enum {
+  CAAR_F_D = 1u << 0,
+  CAAR_F_DINV = 1u << 1,
+  CAAR_F_FCOR = 1u << 2,
+  CAAR_F_SPHEREMP = 1u << 3,
+  CAAR_F_METDET = 1u << 4,
+  CAAR_F_RMETDET = 1u << 5,
+  CAAR_F_DP3D = 1u << 6,
+  CAAR_F_V = 1u << 7,
+  CAAR_F_T = 1u << 8,
+  CAAR_F_PHIS = 1u << 9,
+  CAAR_F_QDP = 1u << 10,
+  CAAR_F_ETA_DOT_DPDN = 1u << 11,
+  CAAR_F_OMEGA_P = 1u << 12,
+  CAAR_F_PHI = 1u << 13,
+  CAAR_F_PECND = 1u << 14,
+  CAAR_F_VN0 = 1u << 15,
+  CAAR_F_ALL = 0xFFFFu,
+  /* the arrays compute_and_apply_rhs writes (PO/compute_and_apply_rhs.cpp:117-118,172-173,251-254,
+     and phi via preq_hydrostatic :161) */
+  CAAR_F_MUTATED = CAAR_F_DP3D | CAAR_F_V | CAAR_F_T | CAAR_F_ETA_DOT_DPDN | CAAR_F_OMEGA_P |
+                   CAAR_F_PHI | CAAR_F_VN0
+};
+#define CAAR_NUM_FIELDS 16
+
+/* Compile-time dimensions of the reference (config.h.in:1-7), made run-time here. */
+typedef struct caar_dims {
+  int nelem;   /* number of elements held by this handle (a rank's slice)      */
+  int nlev;    /* PLEV: 72 or 128 have tuned kernels; others use the generic kernel */
+  int np;      /* must be 4 */
+  int qsize_d; /* QSIZE_D (1 in the reference) */
+  int ntl;     /* NUM_TIME_LEVELS (3) */
+} caar_dims;
+
+/* struct Arrays, PO/data_structures.hpp:18-44 — same members, same order. */
+typedef struct caar_arrays {
+  double* elem_D;        /* [E][4][4][2][2] */
+  double* elem_Dinv;     /* [E][4][4][2][2] */
+  double* elem_fcor;     /* [E][4][4] */
+  double* elem_spheremp; /* [E][4][4] */
+  double* elem_metdet;   /* [E][4][4] */
+  double* elem_rmetdet;  /* [E][4][4] */
+  double* elem_state_dp3d; /* [E][ntl][L][4][4] */
+  double* elem_state_v;    /* [E][ntl][L][4][4][2] */
+  double* elem_state_T;    /* [E][ntl][L][4][4] */
+  double* elem_state_phis; /* [E][4][4] */
+  double* elem_state_Qdp;  /* [E][qsize_d][2][L][4][4] */
+  double* elem_derived_eta_dot_dpdn; /* [E][L+1][4][4] */
+  double* elem_derived_omega_p;      /* [E][L][4][4] */
+  double* elem_derived_phi;          /* [E][L][4][4] */
+  double* elem_derived_pecnd;        /* [E][L][4][4] */
+  double* elem_derived_vn0;          /* [E][L][4][4][2] */
+} caar_arrays;
+
+/* struct Constants, PO/data_structures.hpp:46-56. */
+typedef struct caar_constants {
+  double rrearth;
+  double eta_ave_w;
+  double cp;
+  double Rwater_vapor;
+  double Rgas;
+  double kappa;
+} caar_constants;
+
+/* struct Control, PO/data_structures.hpp:58-69. nets/nete are LOCAL to the handle's slice. */
+typedef struct caar_control {
+  int nets;
+  int nete;
+  int n0;
+  int np1;
+  int nm1;
+  int qn0; /* -1 = dry (T_v = T), else tracer time level index into Qdp[ie][0][qn0] */
+  double dt2;
+} caar_control;
+
+typedef struct caar_handle_s* caar_handle;
+
+/* ---- library ---- */
+const char* caar_last_error(void);
+const char* caar_version(void);
+/* number of doubles in field `field_index` (0..15, order of caar_arrays) for given dims; 0 on bad input */
+size_t caar_field_count(const caar_dims* dims, int field_index);
+/* number of visible CUDA devices, or a negative CAAR_ERR_* */
+int caar_device_count(void);
+
+/* ---- handle lifecycle: one handle per GPU (or per element slice) ---- */
+/* Allocates the device mirrors of all 16 arrays on `device` and creates a stream. */
+int caar_create(caar_handle* out, const caar_dims* dims, int device);
+int caar_destroy(caar_handle h);
+
+/* Constants + Derivative + HVCoord of TestData (PO/data_structures.cpp:117-163). hyai has nlev+1 entries. */
+int caar_set_params(caar_handle h, const caar_constants* c, const double dvv[16], double ps0,
+                    const double* hyai);
+
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all later work; NULL restores the
+   handle's own stream. Lets a torch program time the kernels with its own events. */
+int caar_set_stream(caar_handle h, void* cuda_stream);
+
+/* Host <-> device copies of the selected fields (CAAR_F_* mask). Host pointers are caller-owned and
+   are never freed by the library. Pinned host memory makes these asynchronous DMA copies; both calls
+   return after the copies completed. */
+int caar_upload(caar_handle h, const caar_arrays* host, unsigned field_mask);
+int caar_download(caar_handle h, const caar_arrays* host, unsigned field_mask);
+
+/* Device pointers of the mirrors (for interop, e.g. wrapping in torch tensors, or peer access). */
+int caar_device_arrays(caar_handle h, caar_arrays* dev_out);
+
+/* ---- the hot path ---- */
+/* nsteps back-to-back evaluations of compute_and_apply_rhs on the resident data, asynchronously on the
+   handle's stream. Identical to calling the reference routine nsteps times with the same Control
+   (PO/main.cpp:113-121: no time-level rotation between calls). mode = CAAR_MODE_*. */
+int caar_run(caar_handle h, const caar_control* ctl, int nsteps, int mode);
+int caar_sync(caar_handle h);
+/* number of kernel launches issued by caar_run/caar_norms/saxpby on this handle since creation */
+long long caar_launch_count(caar_handle h);
+
+/* Sum of squares of v, T, dp3d at time level `tl` over elements [nets,nete) — the three quantities
+   print_results_2norm takes the sqrt of (PO/compute_and_apply_rhs.cpp:384-398). Returned as SUMS OF
+   SQUARES so that ranks can all-reduce them before the sqrt. Synchronous. */
+int caar_norms(caar_handle h, int tl, int nets, int nete, double sumsq[3]);
+
+/* Reference-facing one-shot: upload(all) -> run(1) -> download(mutated) on `device`, i.e. exactly what
+   Homme::compute_and_apply_rhs(TestData&) means for host arrays. Creates and destroys a handle. */
+int caar_compute_and_apply_rhs_host(const caar_dims* dims, const caar_arrays* host,
+                                    const caar_control* ctl, const caar_constants* c,
+                                    const double dvv[16], double ps0, const double* hyai, int device,
+                                    int mode);
+
+/* ---- saxpby bandwidth calibrator (saxpby_test/cxx/common.cpp:3-15): x = a*x + b*y ---- */
+/* device pointers, asynchronous on `cuda_stream` (NULL = default stream) */
+int caar_saxpby_device(double a, double b, double* x_dev, const double* y_dev, size_t n,
+                       void* cuda_stream);
+/* host pointers: H2D, `sweeps` sweeps, D2H on `device` */
+int caar_saxpby_host(double a, double b, double* x, const double* y, size_t n, int sweeps, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAAR_B200_H */

@@ -1,0 +1,470 @@
+/* oracle/caar_oracle.c — TEST INFRASTRUCTURE ONLY. NOT part of the product, never linked into
+ * libcaar_b200.so, never called by the product path (only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it).
+ *
+ * A plain-C restatement ("port") of the reference's compute_and_apply_rhs hot path with run-time
+ * nlev, written to round EXACTLY like the reference's `g++ -std=c++11 -O3` x86-64 build: same
+ * operation order, no FMA contraction (built with -ffp-contract=off), IEEE division.
+ *
+ * Parity status: PINNED. tests/test_oracle.py checks this file
+ *   (1) bit-for-bit against the real reference compiled from /root/reference (oracle/_ref, see
+ *       oracle/Makefile) on every mutated array, for PLEV=72 and PLEV=128,
+ *   (2) against the reference's own golden vectors Ttest/v1test/v2test
+ *       (compute_and_apply_rhs_test/fortran/test_mod.F90:8,299,594; committed as tests/golden/*.npy),
+ *   (3) against the norms the reference driver prints (tests/golden/pointers_only_stdout.txt).
+ *
+ * Reference map ("PO/" = compute_and_apply_rhs_test/cxx/pointers_only/):
+ *   grad_sphere()        PO/sphere_operators.cpp:9-48
+ *   div_sphere()         PO/sphere_operators.cpp:50-89
+ *   vort_sphere()        PO/sphere_operators.cpp:91-129
+ *   hydrostatic()        PO/compute_and_apply_rhs.cpp:280-312   (preq_hydrostatic)
+ *   omega_ps()           PO/compute_and_apply_rhs.cpp:314-352   (preq_omega_ps)
+ *   rhs_element()        PO/compute_and_apply_rhs.cpp:74-258    (body of the element loop)
+ *   kahan_norm()         PO/compute_and_apply_rhs.cpp:354-370   (compute_norm)
+ *   caar_oracle_norms()  PO/compute_and_apply_rhs.cpp:372-399   (print_results_2norm)
+ *   caar_oracle_init()   PO/data_structures.cpp:38-92,117-163   (init_data of all five structs)
+ */
+#include "caar_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+enum { NP = 4, PTS = 16 };
+
+enum {
+  F_D, F_DINV, F_FCOR, F_SPHEREMP, F_METDET, F_RMETDET, F_DP3D, F_V, F_T, F_PHIS, F_QDP,
+  F_ETA_DOT_DPDN, F_OMEGA_P, F_PHI, F_PECND, F_VN0
+};
+
+typedef struct {
+  int nlev, qsize_d, ntl;
+  double* const* a;          /* 16 array pointers */
+  int nets, nete, n0, np1, nm1, qn0;
+  double dt2;
+  double rrearth, eta_ave_w, cp, Rwv, Rgas, kappa;
+  const double* dvv;         /* [4][4] row-major */
+  double ps0;
+  const double* hyai;
+} ctx_t;
+
+size_t caar_oracle_field_count(int f, int E, int L, int Q, int ntl) {
+  const size_t e = (size_t)E;
+  switch (f) {
+    case F_D: case F_DINV: return e * PTS * 4;
+    case F_FCOR: case F_SPHEREMP: case F_METDET: case F_RMETDET: case F_PHIS: return e * PTS;
+    case F_DP3D: case F_T: return e * ntl * L * PTS;
+    case F_V: return e * ntl * L * PTS * 2;
+    case F_QDP: return e * Q * 2 * L * PTS;
+    case F_ETA_DOT_DPDN: return e * (L + 1) * PTS;
+    case F_OMEGA_P: case F_PHI: case F_PECND: return e * L * PTS;
+    case F_VN0: return e * L * PTS * 2;
+  }
+  return 0;
+}
+
+/* ---- sphere operators on one 4x4 level of one element ------------------------------------ */
+
+/* ds[i][j][c] = sum over the covariant derivatives, PO/sphere_operators.cpp:21-47 */
+static void grad_sphere(const double* s, const double* dvv, const double* dinv, double rrearth,
+                        double* ds) {
+  double a[NP][NP], b[NP][NP];
+  for (int j = 0; j < NP; ++j)
+    for (int l = 0; l < NP; ++l) {
+      double sx = 0, sy = 0;
+      for (int i = 0; i < NP; ++i) {
+        sx += dvv[i * NP + l] * s[i * NP + j];
+        sy += dvv[i * NP + l] * s[j * NP + i];
+      }
+      a[l][j] = sx * rrearth;
+      b[j][l] = sy * rrearth;
+    }
+  for (int j = 0; j < NP; ++j)
+    for (int i = 0; i < NP; ++i) {
+      const double* di = dinv + (i * NP + j) * 4; /* [2][2] */
+      ds[(i * NP + j) * 2 + 0] = di[0] * a[i][j] + di[2] * b[i][j];
+      ds[(i * NP + j) * 2 + 1] = di[1] * a[i][j] + di[3] * b[i][j];
+    }
+}
+
+/* PO/sphere_operators.cpp:62-88 */
+static void div_sphere(const double* v, const double* dvv, const double* dinv, const double* metdet,
+                       const double* rmetdet, double rrearth, double* div) {
+  double g[NP][NP][2];
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      const double* di = dinv + (i * NP + j) * 4;
+      const double v0 = v[(i * NP + j) * 2], v1 = v[(i * NP + j) * 2 + 1];
+      g[i][j][0] = metdet[i * NP + j] * (di[0] * v0 + di[1] * v1);
+      g[i][j][1] = metdet[i * NP + j] * (di[2] * v0 + di[3] * v1);
+    }
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      double dudx = 0., dvdy = 0.;
+      for (int k = 0; k < NP; ++k) {
+        dudx += dvv[k * NP + i] * g[k][j][0];
+        dvdy += dvv[k * NP + j] * g[i][k][1];
+      }
+      div[i * NP + j] = (dudx + dvdy) * rmetdet[i * NP + j] * rrearth;
+    }
+}
+
+/* PO/sphere_operators.cpp:102-128 */
+static void vort_sphere(const double* v, const double* dvv, const double* d, const double* rmetdet,
+                        double rrearth, double* vort) {
+  double c[NP][NP][2];
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      const double* dd = d + (i * NP + j) * 4;
+      const double v0 = v[(i * NP + j) * 2], v1 = v[(i * NP + j) * 2 + 1];
+      c[i][j][0] = dd[0] * v0 + dd[2] * v1;
+      c[i][j][1] = dd[1] * v0 + dd[3] * v1;
+    }
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      double dudy = 0., dvdx = 0.;
+      for (int k = 0; k < NP; ++k) {
+        dvdx += dvv[k * NP + i] * c[k][j][1];
+        dudy += dvv[k * NP + j] * c[i][k][0];
+      }
+      vort[i * NP + j] = (dvdx - dudy) * rmetdet[i * NP + j] * rrearth;
+    }
+}
+
+/* ---- vertical integrals -------------------------------------------------------------------- */
+
+/* reverse (bottom-up) sum; phii is an [L][16] scratch. PO/compute_and_apply_rhs.cpp:287-311 */
+static void hydrostatic(int L, const double* phis, const double* T_v, const double* p, const double* dp,
+                        double Rgas, double* phii, double* phi) {
+  for (int q = 0; q < PTS; ++q) {
+    int k = L - 1;
+    double hkk = 0.5 * dp[k * PTS + q] / p[k * PTS + q];
+    double hkl = 2.0 * hkk;
+    phii[k * PTS + q] = Rgas * T_v[k * PTS + q] * hkl;
+    phi[k * PTS + q] = phis[q] + Rgas * T_v[k * PTS + q] * hkk;
+    for (k = L - 2; k > 0; --k) {
+      hkk = 0.5 * dp[k * PTS + q] / p[k * PTS + q];
+      hkl = 2.0 * hkk;
+      phii[k * PTS + q] = phii[(k + 1) * PTS + q] + Rgas * T_v[k * PTS + q] * hkl;
+      phi[k * PTS + q] = phis[q] + phii[(k + 1) * PTS + q] + Rgas * T_v[k * PTS + q] * hkk;
+    }
+    hkk = 0.5 * dp[q] / p[q];
+    phi[q] = phis[q] + phii[PTS + q] + Rgas * T_v[q] * hkk;
+  }
+}
+
+/* forward (top-down) running sum of divdp. PO/compute_and_apply_rhs.cpp:319-351 */
+static void omega_ps(int L, const double* p, const double* vgrad_p, const double* divdp, double* omega) {
+  for (int q = 0; q < PTS; ++q) {
+    double ckk = 0.5 / p[q];
+    double term = divdp[q];
+    omega[q] = vgrad_p[q] / p[q] - ckk * term;
+    double suml = term;
+    for (int k = 1; k < L - 1; ++k) {
+      ckk = 0.5 / p[k * PTS + q];
+      const double ckl = 2.0 * ckk;
+      term = divdp[k * PTS + q];
+      omega[k * PTS + q] = vgrad_p[k * PTS + q] / p[k * PTS + q] - ckl * suml - ckk * term;
+      suml += term;
+    }
+    const int k = L - 1;
+    ckk = 0.5 / p[k * PTS + q];
+    const double ckl = 2.0 * ckk;
+    term = divdp[k * PTS + q];
+    omega[k * PTS + q] = vgrad_p[k * PTS + q] / p[k * PTS + q] - ckl * suml - ckk * term;
+  }
+}
+
+/* ---- one element ---------------------------------------------------------------------------- */
+
+typedef struct {
+  double *p, *grad_p, *vgrad_p, *vdp, *divdp, *vort, *T_v, *omega, *phii, *vt1, *vt2, *tt;
+} scratch_t;
+
+static int scratch_alloc(scratch_t* w, int L) {
+  const size_t n = (size_t)L * PTS;
+  double* base = (double*)calloc(n * 14, sizeof(double));
+  if (!base) return -1;
+  w->p = base;            w->grad_p = base + n;      w->vgrad_p = base + 3 * n;
+  w->vdp = base + 4 * n;  w->divdp = base + 6 * n;   w->vort = base + 7 * n;
+  w->T_v = base + 8 * n;  w->omega = base + 9 * n;   w->phii = base + 10 * n;
+  w->vt1 = base + 11 * n; w->vt2 = base + 12 * n;    w->tt = base + 13 * n;
+  return 0;
+}
+
+static void rhs_element(const ctx_t* c, int ie, scratch_t* w) {
+  const int L = c->nlev;
+  const size_t lf = (size_t)L * PTS;                 /* one scalar level-field */
+  double* const* A = c->a;
+  const double* D = A[F_D] + (size_t)ie * PTS * 4;
+  const double* Dinv = A[F_DINV] + (size_t)ie * PTS * 4;
+  const double* fcor = A[F_FCOR] + (size_t)ie * PTS;
+  const double* spheremp = A[F_SPHEREMP] + (size_t)ie * PTS;
+  const double* metdet = A[F_METDET] + (size_t)ie * PTS;
+  const double* rmetdet = A[F_RMETDET] + (size_t)ie * PTS;
+  const double* phis = A[F_PHIS] + (size_t)ie * PTS;
+  const double* dp_n0 = A[F_DP3D] + ((size_t)ie * c->ntl + c->n0) * lf;
+  const double* v_n0 = A[F_V] + ((size_t)ie * c->ntl + c->n0) * lf * 2;
+  const double* T_n0 = A[F_T] + ((size_t)ie * c->ntl + c->n0) * lf;
+  double* vn0 = A[F_VN0] + (size_t)ie * lf * 2;
+  double* phi = A[F_PHI] + (size_t)ie * lf;
+  double* omega_p = A[F_OMEGA_P] + (size_t)ie * lf;
+  double* eta_dot = A[F_ETA_DOT_DPDN] + (size_t)ie * (L + 1) * PTS;
+  const double* pecnd = A[F_PECND] + (size_t)ie * lf;
+
+  /* A: mid-level pressure, top-down (PO:76-97) */
+  for (int q = 0; q < PTS; ++q) w->p[q] = c->hyai[0] * c->ps0 + 0.5 * dp_n0[q];
+  for (int k = 1; k < L; ++k)
+    for (int q = 0; q < PTS; ++q)
+      w->p[k * PTS + q] = w->p[(k - 1) * PTS + q] + 0.5 * dp_n0[(k - 1) * PTS + q] + 0.5 * dp_n0[k * PTS + q];
+
+  /* B: level-local horizontal operators (PO:101-124) */
+  for (int k = 0; k < L; ++k) {
+    double* gp = w->grad_p + (size_t)k * PTS * 2;
+    grad_sphere(w->p + k * PTS, c->dvv, Dinv, c->rrearth, gp);
+    for (int q = 0; q < PTS; ++q) {
+      const double v1 = v_n0[(k * PTS + q) * 2], v2 = v_n0[(k * PTS + q) * 2 + 1];
+      w->vgrad_p[k * PTS + q] = v1 * gp[q * 2] + v2 * gp[q * 2 + 1];
+      w->vdp[(k * PTS + q) * 2] = v1 * dp_n0[k * PTS + q];
+      w->vdp[(k * PTS + q) * 2 + 1] = v2 * dp_n0[k * PTS + q];
+      vn0[(k * PTS + q) * 2] += c->eta_ave_w * w->vdp[(k * PTS + q) * 2];
+      vn0[(k * PTS + q) * 2 + 1] += c->eta_ave_w * w->vdp[(k * PTS + q) * 2 + 1];
+    }
+    div_sphere(w->vdp + (size_t)k * PTS * 2, c->dvv, Dinv, metdet, rmetdet, c->rrearth, w->divdp + k * PTS);
+    vort_sphere(v_n0 + (size_t)k * PTS * 2, c->dvv, D, rmetdet, c->rrearth, w->vort + k * PTS);
+  }
+
+  /* C: virtual temperature (PO:126-156). kappa_star is the constant kappa everywhere. */
+  if (c->qn0 == -1) {
+    for (size_t n = 0; n < lf; ++n) w->T_v[n] = T_n0[n];
+  } else {
+    const double* Qdp = A[F_QDP] + (((size_t)ie * c->qsize_d + 0) * 2 + c->qn0) * lf;
+    for (size_t n = 0; n < lf; ++n) {
+      const double Qt = Qdp[n] / dp_n0[n];
+      w->T_v[n] = T_n0[n] * (1.0 + (c->Rwv / c->Rgas - 1.0) * Qt);
+    }
+  }
+
+  /* D, E: the two vertical integrals (PO:161-162) */
+  hydrostatic(L, phis, w->T_v, w->p, dp_n0, c->Rgas, w->phii, phi);
+  omega_ps(L, w->p, w->vgrad_p, w->divdp, w->omega);
+
+  /* F: accumulate the derived fields (PO:164-183). eta_dot_dpdn_tmp is identically zero. */
+  {
+    const double zero = 0.0;
+    for (size_t n = 0; n < lf; ++n) {
+      eta_dot[n] += c->eta_ave_w * zero;
+      omega_p[n] += c->eta_ave_w * w->omega[n];
+    }
+    for (int q = 0; q < PTS; ++q) eta_dot[lf + q] += c->eta_ave_w * zero;
+  }
+
+  /* G: tendencies (PO:187-234). v_vadv and T_vadv are identically zero in the reference. */
+  for (int k = 0; k < L; ++k) {
+    double Ephi[PTS], gT[PTS * 2], gE[PTS * 2], vgrad_T[PTS];
+    for (int q = 0; q < PTS; ++q) {
+      const double v1 = v_n0[(k * PTS + q) * 2], v2 = v_n0[(k * PTS + q) * 2 + 1];
+      Ephi[q] = 0.5 * (v1 * v1 + v2 * v2) + phi[k * PTS + q] + pecnd[k * PTS + q];
+    }
+    grad_sphere(T_n0 + k * PTS, c->dvv, Dinv, c->rrearth, gT);
+    for (int q = 0; q < PTS; ++q) {
+      const double v1 = v_n0[(k * PTS + q) * 2], v2 = v_n0[(k * PTS + q) * 2 + 1];
+      vgrad_T[q] = v1 * gT[q * 2] + v2 * gT[q * 2 + 1];
+    }
+    grad_sphere(Ephi, c->dvv, Dinv, c->rrearth, gE);
+    const double* gp = w->grad_p + (size_t)k * PTS * 2;
+    for (int q = 0; q < PTS; ++q) {
+      const double v_vadv0 = 0.0, v_vadv1 = 0.0, T_vadv = 0.0;
+      const double gpterm = w->T_v[k * PTS + q] / w->p[k * PTS + q];
+      const double glnps1 = c->Rgas * gpterm * gp[q * 2];
+      const double glnps2 = c->Rgas * gpterm * gp[q * 2 + 1];
+      const double v1 = v_n0[(k * PTS + q) * 2], v2 = v_n0[(k * PTS + q) * 2 + 1];
+      w->vt1[k * PTS + q] = -v_vadv0 + v2 * (fcor[q] + w->vort[k * PTS + q]) - gE[q * 2] - glnps1;
+      w->vt2[k * PTS + q] = -v_vadv1 - v1 * (fcor[q] + w->vort[k * PTS + q]) - gE[q * 2 + 1] - glnps2;
+      w->tt[k * PTS + q] = T_vadv - vgrad_T[q] + c->kappa * w->T_v[k * PTS + q] * w->omega[k * PTS + q];
+    }
+  }
+
+  /* H: apply (PO:236-257) */
+  {
+    double* v_np1 = A[F_V] + ((size_t)ie * c->ntl + c->np1) * lf * 2;
+    double* T_np1 = A[F_T] + ((size_t)ie * c->ntl + c->np1) * lf;
+    double* dp_np1 = A[F_DP3D] + ((size_t)ie * c->ntl + c->np1) * lf;
+    const double* v_nm1 = A[F_V] + ((size_t)ie * c->ntl + c->nm1) * lf * 2;
+    const double* T_nm1 = A[F_T] + ((size_t)ie * c->ntl + c->nm1) * lf;
+    const double* dp_nm1 = A[F_DP3D] + ((size_t)ie * c->ntl + c->nm1) * lf;
+    for (int k = 0; k < L; ++k)
+      for (int q = 0; q < PTS; ++q) {
+        const size_t n = (size_t)k * PTS + q;
+        v_np1[n * 2] = spheremp[q] * (v_nm1[n * 2] + c->dt2 * w->vt1[n]);
+        v_np1[n * 2 + 1] = spheremp[q] * (v_nm1[n * 2 + 1] + c->dt2 * w->vt2[n]);
+        T_np1[n] = spheremp[q] * (T_nm1[n] + c->dt2 * w->tt[n]);
+        dp_np1[n] = spheremp[q] * (dp_nm1[n] - c->dt2 * w->divdp[n]);
+      }
+  }
+}
+
+/* ---- driver ----------------------------------------------------------------------------------- */
+
+typedef struct {
+  ctx_t c;
+  int ncalls;
+} job_t;
+
+static void* worker(void* arg) {
+  job_t* j = (job_t*)arg;
+  scratch_t w;
+  if (scratch_alloc(&w, j->c.nlev)) return (void*)1;
+  for (int n = 0; n < j->ncalls; ++n)
+    for (int ie = j->c.nets; ie < j->c.nete; ++ie) rhs_element(&j->c, ie, &w);
+  free(w.p);
+  return NULL;
+}
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+double caar_oracle_run(int nlev, int qsize_d, int ntl, double* const* arrays, const int* ctl, double dt2,
+                       const double* k6, const double* dvv16, double ps0, const double* hyai, int ncalls,
+                       int nthreads) {
+  ctx_t c;
+  memset(&c, 0, sizeof c);
+  c.nlev = nlev; c.qsize_d = qsize_d; c.ntl = ntl; c.a = arrays;
+  c.nets = ctl[0]; c.nete = ctl[1]; c.n0 = ctl[2]; c.np1 = ctl[3]; c.nm1 = ctl[4]; c.qn0 = ctl[5];
+  c.dt2 = dt2;
+  c.rrearth = k6[0]; c.eta_ave_w = k6[1]; c.cp = k6[2]; c.Rwv = k6[3]; c.Rgas = k6[4]; c.kappa = k6[5];
+  c.dvv = dvv16; c.ps0 = ps0; c.hyai = hyai;
+  const int n = c.nete - c.nets;
+  if (n <= 0 || nlev < 2) return 0.0;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > n) nthreads = n;
+  job_t* jobs = (job_t*)calloc((size_t)nthreads, sizeof(job_t));
+  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t].c = c;
+    jobs[t].ncalls = ncalls;
+    jobs[t].c.nets = c.nets + (int)((long long)n * t / nthreads);
+    jobs[t].c.nete = c.nets + (int)((long long)n * (t + 1) / nthreads);
+  }
+  const double t0 = now_s();
+  if (nthreads == 1) {
+    worker(&jobs[0]);
+  } else {
+    for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, &jobs[t]);
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  }
+  const double t1 = now_s();
+  free(jobs);
+  free(th);
+  return t1 - t0;
+}
+
+/* Kahan-compensated sum of squares, then sqrt (PO:354-370) */
+static double kahan_norm(const double* f, size_t n) {
+  double norm = 0, comp = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double y = f[i] * f[i] - comp;
+    const double t = norm + y;
+    comp = (t - norm) - y;
+    norm = t;
+  }
+  return sqrt(norm);
+}
+
+void caar_oracle_norms(int nlev, int ntl, double* const* arrays, int nets, int nete, int tl, double out[3]) {
+  const size_t lf = (size_t)nlev * PTS;
+  double vn = 0, tn = 0, dn = 0;
+  for (int ie = nets; ie < nete; ++ie) {
+    vn += pow(kahan_norm(arrays[F_V] + ((size_t)ie * ntl + tl) * lf * 2, lf * 2), 2);
+    tn += pow(kahan_norm(arrays[F_T] + ((size_t)ie * ntl + tl) * lf, lf), 2);
+    dn += pow(kahan_norm(arrays[F_DP3D] + ((size_t)ie * ntl + tl) * lf, lf), 2);
+  }
+  out[0] = sqrt(vn);
+  out[1] = sqrt(tn);
+  out[2] = sqrt(dn);
+}
+
+/* closed-form synthetic fields; 1-based index values as in the reference (PO/data_structures.cpp:38-92) */
+void caar_oracle_init(int E, int L, int Q, int ntl, double* const* a, int* ctl, double* dt2, double* k6,
+                      double* dvv16, double* ps0, double* hyai) {
+  for (int f = 0; f < 16; ++f) memset(a[f], 0, caar_oracle_field_count(f, E, L, Q, ntl) * sizeof(double));
+  for (int ie = 0; ie < E; ++ie)
+    for (int i = 0; i < NP; ++i)
+      for (int j = 0; j < NP; ++j) {
+        const double e1 = ie + 1, i1 = i + 1, j1 = j + 1;
+        const size_t q = (size_t)ie * PTS + i * NP + j;
+        a[F_FCOR][q] = sin(i1 + j1);
+        a[F_METDET][q] = i1 * j1;
+        a[F_RMETDET][q] = 1. / a[F_METDET][q];
+        a[F_SPHEREMP][q] = 2 * i1;
+        a[F_PHIS][q] = i1 + j1;
+        a[F_D][q * 4 + 0] = 1.0; a[F_D][q * 4 + 3] = 2.0;
+        a[F_DINV][q * 4 + 0] = 1.0; a[F_DINV][q * 4 + 3] = 0.5;
+        for (int k = 0; k < L; ++k) {
+          const double k1 = k + 1;
+          const size_t n = ((size_t)ie * L + k) * PTS + i * NP + j;
+          a[F_PHI][n] = cos(i1 + 3 * j1) + k1;
+          a[F_VN0][n * 2] = 1.0;
+          a[F_VN0][n * 2 + 1] = 1.0;
+          a[F_PECND][n] = 1.0;
+          a[F_OMEGA_P][n] = j1 * j1;
+          a[F_QDP][(((size_t)ie * Q * 2) * L + k) * PTS + i * NP + j] = 1.0 + sin(i1 * j1 * k1);
+          for (int t = 0; t < ntl; ++t) {
+            const double t1 = t + 1;
+            const size_t m = (((size_t)ie * ntl + t) * L + k) * PTS + i * NP + j;
+            a[F_DP3D][m] = 10.0 * k1 + e1 + i1 + j1 + t1;
+            a[F_V][m * 2] = 1.0 + 0.5 * k1 + i1 + j1 + 0.2 * e1 + 2.0 * t1;
+            a[F_V][m * 2 + 1] = 1.0 + 0.5 * k1 + i1 + j1 + 0.2 * e1 + 3.0 * t1;
+            a[F_T][m] = 1000.0 - k1 - i1 - j1 + 0.1 * e1 + t1;
+          }
+        }
+      }
+  ctl[0] = 0; ctl[1] = E; ctl[2] = 0; ctl[3] = 1; ctl[4] = 2; ctl[5] = 0;
+  *dt2 = 1.0;
+  k6[3] = 461.5;             /* Rwater_vapor */
+  k6[4] = 287.04;            /* Rgas */
+  k6[2] = 1005.0;            /* cp */
+  k6[5] = k6[4] / k6[2];     /* kappa */
+  k6[0] = 1.0 / 6.376e6;     /* rrearth */
+  k6[1] = 1.0;               /* eta_ave_w */
+  *ps0 = 10.0;
+  for (int i = 0; i <= L; ++i) hyai[i] = L + 1 - i;
+  /* GLL derivative matrix for np=4, stored transposed into Dvv (PO/data_structures.cpp:150-163) */
+  static const double vals[16] = {-3.0000000000000000, -0.80901699437494745, 0.30901699437494745,
+                                  -0.50000000000000000, 4.0450849718747373,  0.00000000000000000,
+                                  -1.11803398874989490, 1.54508497187473700, -1.5450849718747370,
+                                  1.11803398874989490,  0.00000000000000000, -4.04508497187473730,
+                                  0.5000000000000000,   -0.30901699437494745, 0.80901699437494745,
+                                  3.000000000000000000};
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) dvv16[i * NP + j] = vals[j * NP + i];
+}
+
+/* ---- saxpby ----------------------------------------------------------------------------------- */
+typedef struct { double a, b; double* x; const double* y; size_t lo, hi; int sweeps; } sax_t;
+static void* sax_worker(void* arg) {
+  sax_t* s = (sax_t*)arg;
+  for (int it = 0; it < s->sweeps; ++it)
+    for (size_t i = s->lo; i < s->hi; ++i) s->x[i] = s->a * s->x[i] + s->b * s->y[i];
+  return NULL;
+}
+double caar_oracle_saxpby(double a, double b, double* x, const double* y, size_t n, int sweeps, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  sax_t* js = (sax_t*)calloc((size_t)nthreads, sizeof(sax_t));
+  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+  const double t0 = now_s();
+  for (int t = 0; t < nthreads; ++t) {
+    js[t].a = a; js[t].b = b; js[t].x = x; js[t].y = y; js[t].sweeps = sweeps;
+    js[t].lo = n * t / nthreads; js[t].hi = n * (t + 1) / nthreads;
+    pthread_create(&th[t], NULL, sax_worker, &js[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  const double t1 = now_s();
+  free(js); free(th);
+  return t1 - t0;
+}

@@ -1,0 +1,254 @@
+"""oracle/harness.py — TEST INFRASTRUCTURE ONLY.
+
+ctypes loaders for the two CPU oracles of the compute_and_apply_rhs path:
+
+  * ``RefOracle(nlev)``  — the REAL reference (compute_and_apply_rhs_test/cxx/pointers_only/*.cpp)
+    compiled by oracle/Makefile into oracle/_ref/libcaar_ref_L<nlev>.so (nlev 72 or 128 only: PLEV is
+    compile-time in the reference, config.h.in:3).
+  * ``PortOracle()``     — our plain-C restatement oracle/caar_oracle.c (any nlev >= 2).
+
+Both expose ``init(nelem)`` (the reference's closed-form synthetic data, PO/data_structures.cpp:38-92),
+``run(state, ncalls, nthreads)`` (PO/compute_and_apply_rhs.cpp:15-278) and ``norms(state)``
+(PO/compute_and_apply_rhs.cpp:372-399) on a ``State`` of numpy arrays in the reference's host layout.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+FIELD_NAMES = (
+    "elem_D", "elem_Dinv", "elem_fcor", "elem_spheremp", "elem_metdet", "elem_rmetdet",
+    "elem_state_dp3d", "elem_state_v", "elem_state_T", "elem_state_phis", "elem_state_Qdp",
+    "elem_derived_eta_dot_dpdn", "elem_derived_omega_p", "elem_derived_phi", "elem_derived_pecnd",
+    "elem_derived_vn0",
+)
+MUTATED = ("elem_state_dp3d", "elem_state_v", "elem_state_T", "elem_derived_eta_dot_dpdn",
+           "elem_derived_omega_p", "elem_derived_phi", "elem_derived_vn0")
+
+
+def field_shape(name: str, E: int, L: int, Q: int = 1, ntl: int = 3):
+    """Host shapes, PO/data_structures.cpp:14-31."""
+    return {
+        "elem_D": (E, 4, 4, 2, 2), "elem_Dinv": (E, 4, 4, 2, 2),
+        "elem_fcor": (E, 4, 4), "elem_spheremp": (E, 4, 4), "elem_metdet": (E, 4, 4),
+        "elem_rmetdet": (E, 4, 4), "elem_state_phis": (E, 4, 4),
+        "elem_state_dp3d": (E, ntl, L, 4, 4), "elem_state_T": (E, ntl, L, 4, 4),
+        "elem_state_v": (E, ntl, L, 4, 4, 2),
+        "elem_state_Qdp": (E, Q, 2, L, 4, 4),
+        "elem_derived_eta_dot_dpdn": (E, L + 1, 4, 4),
+        "elem_derived_omega_p": (E, L, 4, 4), "elem_derived_phi": (E, L, 4, 4),
+        "elem_derived_pecnd": (E, L, 4, 4), "elem_derived_vn0": (E, L, 4, 4, 2),
+    }[name]
+
+
+@dataclass
+class State:
+    """A TestData (PO/data_structures.hpp:78-89) as numpy arrays + scalars."""
+    nelem: int
+    nlev: int
+    qsize_d: int = 1
+    ntl: int = 3
+    arrays: dict = field(default_factory=dict)
+    # Control (nets, nete, n0, np1, nm1, qn0) + dt2
+    ctl: np.ndarray = None
+    dt2: float = 1.0
+    # Constants (rrearth, eta_ave_w, cp, Rwater_vapor, Rgas, kappa)
+    consts: np.ndarray = None
+    dvv: np.ndarray = None      # (4,4) row-major, Dvv[i][j]
+    ps0: float = 10.0
+    hyai: np.ndarray = None     # (nlev+1,)
+
+    @classmethod
+    def empty(cls, nelem, nlev, qsize_d=1, ntl=3):
+        s = cls(nelem, nlev, qsize_d, ntl)
+        for n in FIELD_NAMES:
+            s.arrays[n] = np.zeros(field_shape(n, nelem, nlev, qsize_d, ntl), dtype=np.float64)
+        s.ctl = np.zeros(6, dtype=np.int32)
+        s.consts = np.zeros(6, dtype=np.float64)
+        s.dvv = np.zeros((4, 4), dtype=np.float64)
+        s.hyai = np.zeros(nlev + 1, dtype=np.float64)
+        return s
+
+    def copy(self):
+        s = State(self.nelem, self.nlev, self.qsize_d, self.ntl)
+        s.arrays = {k: v.copy() for k, v in self.arrays.items()}
+        s.ctl = self.ctl.copy()
+        s.dt2 = self.dt2
+        s.consts = self.consts.copy()
+        s.dvv = self.dvv.copy()
+        s.ps0 = self.ps0
+        s.hyai = self.hyai.copy()
+        return s
+
+    def ptr_table(self):
+        tab = (C.POINTER(C.c_double) * 16)()
+        for i, n in enumerate(FIELD_NAMES):
+            a = self.arrays[n]
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+            tab[i] = a.ctypes.data_as(C.POINTER(C.c_double))
+        return tab
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def build_port(force=False):
+    so = os.path.join(HERE, "libcaar_oracle.so")
+    src = os.path.join(HERE, "caar_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "port"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def build_ref(force=False):
+    """Builds oracle/_ref from /root/reference when that exists (this container); on the GPU box the
+    prebuilt files shipped in oracle/_ref are used as they are."""
+    if os.path.isdir("/root/reference/compute_and_apply_rhs_test"):
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    return REF_DIR
+
+
+def ref_available(nlev=72):
+    return os.path.exists(os.path.join(REF_DIR, f"libcaar_ref_L{nlev}.so"))
+
+
+class PortOracle:
+    kind = "port"
+
+    def __init__(self):
+        self.lib = C.CDLL(build_port())
+        L = self.lib
+        L.caar_oracle_run.restype = C.c_double
+        L.caar_oracle_saxpby.restype = C.c_double
+        L.caar_oracle_field_count.restype = C.c_size_t
+
+    def init(self, nelem, nlev=72, qsize_d=1, ntl=3) -> State:
+        s = State.empty(nelem, nlev, qsize_d, ntl)
+        dt2, ps0 = C.c_double(), C.c_double()
+        self.lib.caar_oracle_init(nelem, nlev, qsize_d, ntl, s.ptr_table(), _ip(s.ctl), C.byref(dt2),
+                                  _dp(s.consts), _dp(s.dvv), C.byref(ps0), _dp(s.hyai))
+        s.dt2, s.ps0 = dt2.value, ps0.value
+        return s
+
+    def run(self, s: State, ncalls=1, nthreads=1) -> float:
+        return self.lib.caar_oracle_run(s.nlev, s.qsize_d, s.ntl, s.ptr_table(), _ip(s.ctl),
+                                        C.c_double(s.dt2), _dp(s.consts), _dp(s.dvv), C.c_double(s.ps0),
+                                        _dp(s.hyai), ncalls, nthreads)
+
+    def norms(self, s: State, tl=None):
+        out = np.zeros(3)
+        tl = int(s.ctl[3]) if tl is None else tl
+        self.lib.caar_oracle_norms(s.nlev, s.ntl, s.ptr_table(), int(s.ctl[0]), int(s.ctl[1]), tl, _dp(out))
+        return out
+
+    def saxpby(self, a, b, x, y, sweeps=1, nthreads=1) -> float:
+        return self.lib.caar_oracle_saxpby(C.c_double(a), C.c_double(b), _dp(x), _dp(y), C.c_size_t(x.size),
+                                           sweeps, nthreads)
+
+
+class RefOracle:
+    kind = "reference"
+
+    def __init__(self, nlev=72):
+        path = os.path.join(REF_DIR, f"libcaar_ref_L{nlev}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.caar_ref_run.restype = C.c_double
+        self.nlev = self.lib.caar_ref_nlev()
+        assert self.nlev == nlev
+
+    def init(self, nelem, nlev=None, qsize_d=1, ntl=3) -> State:
+        assert nlev in (None, self.nlev) and qsize_d == 1 and ntl == 3
+        s = State.empty(nelem, self.nlev)
+        dt2, ps0 = C.c_double(), C.c_double()
+        self.lib.caar_ref_init(nelem, s.ptr_table(), _ip(s.ctl), C.byref(dt2), _dp(s.consts), _dp(s.dvv),
+                               C.byref(ps0), _dp(s.hyai))
+        s.dt2, s.ps0 = dt2.value, ps0.value
+        return s
+
+    def run(self, s: State, ncalls=1, nthreads=1) -> float:
+        assert s.nlev == self.nlev and s.qsize_d == 1 and s.ntl == 3
+        return self.lib.caar_ref_run(s.ptr_table(), _ip(s.ctl), C.c_double(s.dt2), _dp(s.consts), _dp(s.dvv),
+                                     C.c_double(s.ps0), _dp(s.hyai), ncalls, nthreads)
+
+    def norms(self, s: State, tl=None):
+        out = np.zeros(3)
+        tl = int(s.ctl[3]) if tl is None else tl
+        self.lib.caar_ref_norms(s.ptr_table(), int(s.ctl[0]), int(s.ctl[1]), tl, _dp(out))
+        return out
+
+
+class RefSaxpby:
+    def __init__(self):
+        path = os.path.join(REF_DIR, "libsaxpby_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.saxpby_ref_run.restype = C.c_double
+
+    def run(self, a, b, x, y, sweeps=1) -> float:
+        i1 = x.size // (128 * 256)
+        assert i1 * 128 * 256 == x.size
+        return self.lib.saxpby_ref_run(C.c_double(a), C.c_double(b), _dp(x), _dp(y), i1, sweeps)
+
+
+def best_oracle(nlev=72):
+    """The real reference when its prebuilt library is present, else the restatement."""
+    if ref_available(nlev):
+        return RefOracle(nlev)
+    return PortOracle()
+
+
+def randomize(s: State, seed=20261018):
+    """Non-trivial geometry and fields for parity tests, in the spirit of the reference's own random
+    bench init (level_vectorized_ppscan/Elements.cpp:101-152: U(1/64,1) fields, |det D| >= 1/64,
+    Dinv = D^-1) but with a fixed seed and physically-scaled magnitudes."""
+    rng = np.random.default_rng(seed)
+    E, L = s.nelem, s.nlev
+    A = s.arrays
+    D = rng.uniform(-1.0, 1.0, size=(E, 4, 4, 2, 2))
+    det = D[..., 0, 0] * D[..., 1, 1] - D[..., 0, 1] * D[..., 1, 0]
+    bad = np.abs(det) < 1.0 / 64
+    D[bad] = np.array([[1.0, 0.25], [-0.25, 0.75]])
+    det = D[..., 0, 0] * D[..., 1, 1] - D[..., 0, 1] * D[..., 1, 0]
+    Dinv = np.empty_like(D)
+    Dinv[..., 0, 0] = D[..., 1, 1] / det
+    Dinv[..., 0, 1] = -D[..., 0, 1] / det
+    Dinv[..., 1, 0] = -D[..., 1, 0] / det
+    Dinv[..., 1, 1] = D[..., 0, 0] / det
+    A["elem_D"][...] = D
+    A["elem_Dinv"][...] = Dinv
+    A["elem_metdet"][...] = np.abs(det)
+    A["elem_rmetdet"][...] = 1.0 / np.abs(det)
+    A["elem_fcor"][...] = rng.uniform(-1.4e-4, 1.4e-4, size=(E, 4, 4))
+    A["elem_spheremp"][...] = rng.uniform(1.0 / 64, 1.0, size=(E, 4, 4))
+    A["elem_state_phis"][...] = rng.uniform(0.0, 3.0e3, size=(E, 4, 4))
+    A["elem_state_dp3d"][...] = rng.uniform(5.0, 15.0, size=A["elem_state_dp3d"].shape)
+    A["elem_state_v"][...] = rng.uniform(-40.0, 40.0, size=A["elem_state_v"].shape)
+    A["elem_state_T"][...] = rng.uniform(200.0, 300.0, size=A["elem_state_T"].shape)
+    A["elem_state_Qdp"][...] = rng.uniform(0.0, 0.02, size=A["elem_state_Qdp"].shape) * 10.0
+    A["elem_derived_eta_dot_dpdn"][...] = rng.uniform(-1.0, 1.0, size=A["elem_derived_eta_dot_dpdn"].shape)
+    A["elem_derived_omega_p"][...] = rng.uniform(-1.0, 1.0, size=A["elem_derived_omega_p"].shape)
+    A["elem_derived_phi"][...] = rng.uniform(0.0, 1.0, size=A["elem_derived_phi"].shape)
+    A["elem_derived_pecnd"][...] = rng.uniform(-10.0, 10.0, size=A["elem_derived_pecnd"].shape)
+    A["elem_derived_vn0"][...] = rng.uniform(-1.0, 1.0, size=A["elem_derived_vn0"].shape)
+    s.consts[1] = 0.25  # eta_ave_w != 1 exercises the accumulators
+    s.dt2 = 37.5
+    s.ps0 = 1.0e3
+    s.hyai[...] = np.linspace(0.002, 0.0, L + 1)
+    return s

@@ -1,0 +1,139 @@
+"""Pins the CPU oracle (oracle/caar_oracle.c) before anything is compared with it:
+
+  1. the reference's own golden vectors (fortran/test_mod.F90, committed as tests/golden/fortran_golden.npz),
+  2. the norms the unmodified reference driver prints (tests/golden/pointers_only_stdout.txt),
+  3. the real reference compiled from /root/reference (oracle/_ref/*.so), bit for bit, when present,
+  4. committed outputs of the real reference (tests/golden/ref_outputs_E3.npz) — always.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import harness
+
+
+def test_golden_fortran_vectors(port, golden_dir):
+    """Reference KAT: fortran/main.F90:241-274 compares T, v1, v2 of element 1 at np1 with
+    Ttest/v1test/v2test. The Fortran driver fills Dvv from single-precision literals
+    (fortran/main.F90:79-90), so Dvv is rounded through float32 here."""
+    g = np.load(os.path.join(golden_dir, "fortran_golden.npz"))
+    s = port.init(3)                                # nelemd = 3 is the Fortran default (kinds.F90:21)
+    s.dvv[...] = s.dvv.astype(np.float32).astype(np.float64)
+    port.run(s)
+    np1 = int(s.ctl[3])
+    # golden order: i fastest, then j, then k  <->  C [k][igp=i][jgp=j]
+    T = s.arrays["elem_state_T"][0, np1].transpose(0, 2, 1).reshape(-1)
+    v1 = s.arrays["elem_state_v"][0, np1, ..., 0].transpose(0, 2, 1).reshape(-1)
+    v2 = s.arrays["elem_state_v"][0, np1, ..., 1].transpose(0, 2, 1).reshape(-1)
+    assert np.array_equal(T, g["Ttest"])            # 17 significant digits printed: bit-exact
+    # v literals carry 15 significant digits
+    assert np.max(np.abs(v1 - g["v1test"]) / np.abs(g["v1test"])) < 1e-14
+    assert np.max(np.abs(v2 - g["v2test"]) / np.abs(g["v2test"])) < 1e-14
+
+
+def test_golden_fortran_vectors_double_dvv(port, golden_dir):
+    """With the C++ drivers' double-precision Dvv the same vectors are matched to the float rounding of Dvv."""
+    g = np.load(os.path.join(golden_dir, "fortran_golden.npz"))
+    s = port.init(3)
+    port.run(s)
+    T = s.arrays["elem_state_T"][0, 1].transpose(0, 2, 1).reshape(-1)
+    assert np.max(np.abs(T - g["Ttest"]) / np.abs(g["Ttest"])) < 1e-11
+
+
+def test_printed_norms_of_reference_driver(port, golden_dir):
+    """pointers_only/main.cpp:105,131 print ||v||,||T||,||dp|| before and after one call on 10 elements."""
+    txt = open(os.path.join(golden_dir, "pointers_only_stdout.txt")).read()
+    vals = [float(x) for x in re.findall(r"=\s*([0-9.eE+-]+)", txt)]
+    assert len(vals) == 6
+    s = port.init(10)
+    n0 = port.norms(s)
+    port.run(s)
+    n1 = port.norms(s)
+    assert np.array_equal(n0, np.array(vals[:3]))
+    assert np.array_equal(n1, np.array(vals[3:]))
+
+
+def test_committed_reference_outputs(port, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_outputs_E3.npz"))
+    s = port.init(3)
+    for call in (1, 2):
+        port.run(s)
+        for n in harness.MUTATED:
+            a = s.arrays[n]
+            if n in ("elem_state_dp3d", "elem_state_v", "elem_state_T"):
+                a = a[:, int(s.ctl[3])]
+            assert np.array_equal(a, g[f"call{call}_{n}"]), (call, n)
+
+
+@pytest.mark.parametrize("nlev", [72, 128])
+def test_port_bit_identical_to_compiled_reference(port, nlev):
+    if not harness.ref_available(nlev):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ro = harness.RefOracle(nlev)
+    a, b = port.init(4, nlev), ro.init(4)
+    for n in harness.FIELD_NAMES:
+        assert np.array_equal(a.arrays[n], b.arrays[n]), n
+    assert np.array_equal(a.dvv, b.dvv) and np.array_equal(a.hyai, b.hyai)
+    assert np.array_equal(a.consts, b.consts) and np.array_equal(a.ctl, b.ctl)
+    port.run(a, 2, 1)
+    ro.run(b, 2, 1)
+    for n in harness.FIELD_NAMES:
+        assert np.array_equal(a.arrays[n], b.arrays[n]), n
+    assert np.array_equal(port.norms(a), ro.norms(b))
+    # random geometry/fields, dry and moist, a rotated set of time levels, threads on both sides
+    for qn0, tls in ((0, (0, 1, 2)), (-1, (2, 0, 1)), (1, (1, 2, 0))):
+        a = harness.randomize(port.init(5, nlev), seed=7 + qn0)
+        a.ctl[2:5] = tls
+        a.ctl[5] = qn0
+        b = a.copy()
+        port.run(a, 1, 2)
+        ro.run(b, 1, 3)
+        for n in harness.FIELD_NAMES:
+            assert np.array_equal(a.arrays[n], b.arrays[n]), (qn0, n)
+
+
+def test_inputs_untouched_and_partition(port):
+    """Only the arrays of PO/compute_and_apply_rhs.cpp:117-118,172-173,251-254 (+phi) change, only at np1,
+    only inside [nets,nete)."""
+    s = harness.randomize(port.init(6))
+    ref = s.copy()
+    s.ctl[0], s.ctl[1] = 2, 5
+    port.run(s)
+    for n in harness.FIELD_NAMES:
+        if n not in harness.MUTATED:
+            assert np.array_equal(s.arrays[n], ref.arrays[n]), n
+    for n in harness.MUTATED:
+        a, b = s.arrays[n], ref.arrays[n]
+        assert np.array_equal(a[:2], b[:2]) and np.array_equal(a[5:], b[5:]), n
+    for n in ("elem_state_dp3d", "elem_state_v", "elem_state_T"):
+        assert np.array_equal(s.arrays[n][:, 0], ref.arrays[n][:, 0])
+        assert np.array_equal(s.arrays[n][:, 2], ref.arrays[n][:, 2])
+        assert not np.array_equal(s.arrays[n][2:5, 1], ref.arrays[n][2:5, 1])
+    # running [0,6) in one go == running three disjoint ranges
+    full = ref.copy()
+    port.run(full)
+    parts = ref.copy()
+    for lo, hi in ((0, 1), (1, 4), (4, 6)):
+        parts.ctl[0], parts.ctl[1] = lo, hi
+        port.run(parts)
+    for n in harness.MUTATED:
+        assert np.array_equal(full.arrays[n], parts.arrays[n]), n
+
+
+def test_saxpby_port():
+    po = harness.PortOracle()
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(1 << 16), rng.standard_normal(1 << 16)
+    want = x.copy()
+    for _ in range(3):
+        want = 3.0 * want + 5.0 * y
+    po.saxpby(3.0, 5.0, x, y, sweeps=3, nthreads=2)
+    assert np.array_equal(x, want)
+    if os.path.exists(os.path.join(harness.REF_DIR, "libsaxpby_ref.so")):
+        x2 = rng.standard_normal(2 * 128 * 256)
+        y2 = rng.standard_normal(2 * 128 * 256)
+        w2 = 3.0 * x2 + 5.0 * y2
+        harness.RefSaxpby().run(3.0, 5.0, x2, y2, 1)
+        assert np.array_equal(x2, w2)
