@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — compute_and_apply_rhs element·level updates per second on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's own CPU implementation on the host cores
+
+A "step" = one compute_and_apply_rhs over every element this job holds. Workload = BASELINE configs[3]:
+ne=120 cubed sphere (86400 elements), np=4, nlev=72, FP64 — per GPU (weak scaling: the element loop has no
+inter-element coupling, each rank owns a contiguous element range, no collective in the timed loop; NCCL is
+used only for the max-over-ranks time and the final all-reduce of the squared norms).
+
+One JSON line on stdout (rank 0). `value` = whole-job updates/s with state resident in HBM (CUDA events on
+the launching stream); `e2e` = the same through the reference-facing host call (pinned host arrays, H2D of
+inputs and D2H of results inside the timed region); `roofline` = achieved algorithmic HBM GB/s of the fused
+kernel against the measured copy peak; `cpu_baseline` = the reference CPU build on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "compute_and_apply_rhs_elem_lev_updates_per_s"
+UNIT = "elem*lev updates/s"
+NE120 = 86400
+
+
+def b_alg(nlev: int) -> float:
+    """Algorithmic (compulsory) HBM bytes per element·level, SURVEY.md §8(d)/DESIGN.md: 13 level-fields read
+    + 8 written (21 x 128 B) + 1664 B of per-element 2-D geometry amortised over the levels."""
+    return 21 * 128.0 + 1664.0 / nlev
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch(nelem, nlev):
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, scaled to this
+    launch's element count (traffic is linear in elements); None until a capture exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if int(t["nlev"]) != nlev:
+            return None
+        return float(t["dram_bytes_per_elem"]) * nelem
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_rate(nlev, target_s=15.0, threads=None, calls=None):
+    """The reference's own CPU implementation (oracle/_ref when built from /root/reference, else the C port)
+    on `threads` host threads over a bounded sample: 256 elements per thread, enough calls for ~target_s."""
+    from oracle import harness
+    orc = harness.best_oracle(nlev)
+    threads = threads or cpu_threads()
+    E = 256 * threads
+    s = orc.init(E, nlev)
+    t1 = orc.run(s, 1, threads)                       # also warms the pages
+    if calls is None:
+        calls = max(1, min(200, int(target_s / max(t1, 1e-6))))
+    t = orc.run(s, calls, threads)
+    rate = E * nlev * calls / t
+    sample = (f"{E} elements (256 per thread) x {calls} calls, nlev={nlev}, closed-form init, "
+              f"{threads} threads on disjoint [nets,nete) ranges, wall clock {t:.2f}s")
+    return rate, orc.kind, threads, sample, t / calls
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = cpu_threads()
+    from oracle import harness
+    orc = harness.best_oracle(args.nlev)
+    E = 512 * threads
+    calls = 2                                   # per step: amortises the per-step thread start-up
+    s = orc.init(E, args.nlev)
+    for _ in range(max(1, args.warmup)):
+        orc.run(s, calls, threads)
+    # each step = `calls` passes over the bounded sample; the whole run ends within a few minutes
+    steps = args.steps
+    t0 = time.perf_counter()
+    total = 0.0
+    for _ in range(steps):
+        total += orc.run(s, calls, threads)
+    wall = time.perf_counter() - t0
+    rate = E * args.nlev * steps * calls / total
+    sample = (f"{E} elements (512 per thread) x {calls} calls per step, nlev={args.nlev}, closed-form init, "
+              f"{threads} threads on disjoint [nets,nete) ranges; the rate is per unit, so it stands for the "
+              f"{args.nelem}-element workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference closed-form init)",
+        "config": {"workload": f"ne=120 cubed sphere: {args.nelem} elements per GPU, np=4, nlev={args.nlev}, FP64",
+                   "sampled": True},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": orc.kind, "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nelem", type=int, default=NE120, help="elements per GPU (default ne=120: 86400)")
+    ap.add_argument("--nlev", type=int, default=72)
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-target-s", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import tinman_sandbox_b200 as tb
+    from tinman_sandbox_b200.testdata import TestData
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    E, L = args.nelem, args.nlev
+    mode = tb.MODE_FAST if args.mode == "fast" else tb.MODE_STRICT
+
+    # ---- synthetic inputs: the reference's closed-form init for this rank's element range, in pinned memory
+    pinned = []
+
+    def alloc(shape):
+        n = int(np.prod(shape))
+        try:
+            t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        except Exception:
+            t = torch.empty(n, dtype=torch.float64)
+        pinned.append(t)
+        return t.numpy().reshape(shape)
+
+    td = TestData(E, L, alloc=alloc).init_data(elem_offset=rank * E)
+    h = tb.Caar(E, L, device=local_rank)
+    h.set_params(td.consts, td.dvv, td.ps0, td.hyai)
+    h.set_control(*[int(x) for x in td.ctl], dt2=td.dt2)
+    h.upload(td.arrays)
+
+    # ---- resident-state throughput: W warm-up steps, then exactly K steps between CUDA events
+    h.compute_and_apply_rhs(args.warmup, mode)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = h.launch_count()
+    h.timer_start()
+    h.compute_and_apply_rhs(args.steps, mode, sync=False)
+    ms = h.timer_stop()
+    barrier()
+    launches = h.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    ms_per_step = ms_max / args.steps
+    value = world * E * L * args.steps / (ms_max * 1e-3)
+
+    # ---- norms: the only collective of the job (sum of squares all-reduced over NVLink, then sqrt)
+    ss = torch.from_numpy(h.sumsq(int(td.ctl[3]))).to(dev)
+    if world > 1:
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+    norms = torch.sqrt(ss).cpu().numpy().tolist()
+
+    # ---- end to end through the reference-facing host semantics: host arrays in, host arrays out, per step
+    e2e = None
+    if not args.no_e2e:
+        from tinman_sandbox_b200.capi import FIELD_NAMES, MUTATED_FIELDS
+        n0, np1, nm1, qn0 = [int(x) for x in td.ctl[2:6]]
+        ins = [n for n in FIELD_NAMES if n != "elem_derived_eta_dot_dpdn" or mode == tb.MODE_STRICT]
+        outs = [n for n in MUTATED_FIELDS if n != "elem_derived_eta_dot_dpdn" or mode == tb.MODE_STRICT]
+        h2d = sum(td.arrays[n].nbytes for n in ins)
+        d2h = sum(td.arrays[n].nbytes for n in outs)
+        h.upload(td.arrays, ins)
+        h.compute_and_apply_rhs(1, mode)
+        h.download(td.arrays, outs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            h.upload(td.arrays, ins)
+            h.compute_and_apply_rhs(1, mode)
+            h.download(td.arrays, outs)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * E * L * args.e2e_steps / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "how": "caar_upload(all inputs, pinned host) + caar_run + caar_download(mutated arrays) per step"}
+    h.close()
+
+    # ---- roofline of the dominant (only) kernel of a step
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = b_alg(L) * E * L
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_per_launch(E, L), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8000": achieved / 8000.0,
+                "kernel": "caar_fused_kernel" if mode == tb.MODE_FAST else "caar_strict_kernel"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, kind, cores, sample, _ = cpu_reference_rate(L, target_s=args.cpu_target_s)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference closed-form init)",
+            "config": {"workload": f"ne=120 cubed sphere: {E} elements per GPU, np=4, nlev={L}, FP64, "
+                                   f"n0/np1/nm1 distinct, qn0=0",
+                       "elements_per_gpu": E, "nlev": L, "mode": args.mode,
+                       "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" %
+                             (sum(a.nbytes for a in td.arrays.values()) / 1e9)},
+            "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "clocks": clocks, "norms_np1": norms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -174,8 +174,12 @@ int caar_device_arrays(caar_handle h, caar_arrays* dev_out);
    (PO/main.cpp:113-121: no time-level rotation between calls). mode = CAAR_MODE_*. */
 int caar_run(caar_handle h, const caar_control* ctl, int nsteps, int mode);
 int caar_sync(caar_handle h);
-/* number of kernel launches issued by caar_run/caar_norms/saxpby on this handle since creation */
+/* number of kernel launches issued by caar_run/caar_norms on this handle since creation */
 long long caar_launch_count(caar_handle h);
+/* CUDA-event stopwatch on the stream the kernels are launched on: start records an event, stop records a
+   second one, waits for it and returns the device time between the two in milliseconds. */
+int caar_timer_start(caar_handle h);
+int caar_timer_stop(caar_handle h, float* ms);
 
 /* Sum of squares of v, T, dp3d at time level `tl` over elements [nets,nete) — the three quantities
    print_results_2norm takes the sqrt of (PO/compute_and_apply_rhs.cpp:384-398). Returned as SUMS OF

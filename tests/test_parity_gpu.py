@@ -1,0 +1,211 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+inputs. Tolerance (BASELINE.json north_star): relative 1e-12 per field, measured as
+max|a-b| / max|b| over the field; the strict kernel must be bit-identical."""
+import os
+
+import numpy as np
+import pytest
+
+import tinman_sandbox_b200 as tb
+from oracle import harness
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def oracle_for(nlev):
+    return harness.best_oracle(nlev) if nlev in (72, 128) else harness.PortOracle()
+
+
+def run_gpu(state, ncalls=1, mode=tb.MODE_FAST):
+    h = tb.Caar(state.nelem, state.nlev, state.qsize_d, state.ntl)
+    h.set_params(state.consts, state.dvv, state.ps0, state.hyai)
+    h.set_control(*[int(x) for x in state.ctl], dt2=state.dt2)
+    h.upload(state.arrays)
+    h.compute_and_apply_rhs(ncalls, mode)
+    h.download(state.arrays, names=None)
+    nrm = h.norms()
+    h.close()
+    return nrm
+
+
+def check(got, want, exact):
+    for n in harness.FIELD_NAMES:
+        if n not in harness.MUTATED or exact:
+            assert np.array_equal(got.arrays[n], want.arrays[n]), n
+        else:
+            assert rel_err(got.arrays[n], want.arrays[n]) <= TOL, (n, rel_err(got.arrays[n], want.arrays[n]))
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+def test_reference_default_config(mode):
+    """BASELINE configs[0]: the cxx driver default, 10 elements, 1 call."""
+    orc = oracle_for(72)
+    want = orc.init(10)
+    got = want.copy()
+    orc.run(want)
+    nrm = run_gpu(got, 1, mode)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+    assert np.max(np.abs(nrm - orc.norms(want)) / orc.norms(want)) < 1e-13
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+def test_golden_fortran_vectors(mode, golden_dir):
+    """The reference's own KAT (fortran/test_mod.F90) straight against the CUDA path."""
+    g = np.load(os.path.join(golden_dir, "fortran_golden.npz"))
+    s = harness.PortOracle().init(3)
+    s.dvv[...] = s.dvv.astype(np.float32).astype(np.float64)
+    run_gpu(s, 1, mode)
+    T = s.arrays["elem_state_T"][0, 1].transpose(0, 2, 1).reshape(-1)
+    v1 = s.arrays["elem_state_v"][0, 1, ..., 0].transpose(0, 2, 1).reshape(-1)
+    v2 = s.arrays["elem_state_v"][0, 1, ..., 1].transpose(0, 2, 1).reshape(-1)
+    if mode == tb.MODE_STRICT:
+        assert np.array_equal(T, g["Ttest"])
+    assert rel_err(T, g["Ttest"]) < TOL and rel_err(v1, g["v1test"]) < TOL and rel_err(v2, g["v2test"]) < TOL
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+def test_committed_reference_outputs(mode, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_outputs_E3.npz"))
+    s = harness.PortOracle().init(3)
+    for call in (1, 2):
+        run_gpu(s, 1, mode)
+        for n in harness.MUTATED:
+            a = s.arrays[n]
+            if n in ("elem_state_dp3d", "elem_state_v", "elem_state_T"):
+                a = a[:, 1]
+            if mode == tb.MODE_STRICT:
+                assert np.array_equal(a, g[f"call{call}_{n}"]), (call, n)
+            else:
+                assert rel_err(a, g[f"call{call}_{n}"]) <= TOL, (call, n)
+
+
+@pytest.mark.parametrize("nlev", [72, 128])
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+@pytest.mark.parametrize("qn0,tls", [(0, (0, 1, 2)), (-1, (2, 0, 1)), (1, (1, 2, 0))])
+def test_random_fields(nlev, mode, qn0, tls):
+    """Random geometry and fields, moist and dry, rotated time levels, eta_ave_w != 1, 3 calls (accumulators)."""
+    orc = oracle_for(nlev)
+    want = harness.randomize(harness.PortOracle().init(37, nlev), seed=100 + nlev + qn0)
+    want.ctl[2:5] = tls
+    want.ctl[5] = qn0
+    got = want.copy()
+    orc.run(want, 3, 4)
+    run_gpu(got, 3, mode)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+@pytest.mark.parametrize("n0,np1,nm1", [(0, 0, 0), (0, 1, 0), (0, 1, 1), (1, 0, 0)])
+def test_time_level_aliasing(mode, n0, np1, nm1):
+    """nm1 = np1 = n0 (forward Euler / RK stages) must behave like the reference."""
+    orc = oracle_for(72)
+    want = harness.randomize(harness.PortOracle().init(9), seed=5)
+    want.ctl[2:5] = (n0, np1, nm1)
+    got = want.copy()
+    orc.run(want, 2, 1)
+    run_gpu(got, 2, mode)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+def test_element_range_partition(mode):
+    """nets/nete: only [nets,nete) changes; disjoint ranges compose to the full run (the multi-GPU split)."""
+    orc = oracle_for(72)
+    base = harness.randomize(harness.PortOracle().init(11), seed=9)
+    want = base.copy()
+    want.ctl[0], want.ctl[1] = 3, 8
+    got = want.copy()
+    orc.run(want)
+    run_gpu(got, 1, mode)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+    for n in harness.MUTATED:
+        assert np.array_equal(got.arrays[n][:3], base.arrays[n][:3])
+        assert np.array_equal(got.arrays[n][8:], base.arrays[n][8:])
+
+
+@pytest.mark.parametrize("nlev", [8, 16, 24, 64, 100])
+def test_other_level_counts(nlev):
+    """nlev without a fused-kernel instance falls back to the generic strict kernel — still on the GPU."""
+    orc = harness.PortOracle()
+    want = harness.randomize(orc.init(5, nlev), seed=nlev)
+    gs, gf = want.copy(), want.copy()
+    orc.run(want)
+    run_gpu(gs, 1, tb.MODE_STRICT)
+    run_gpu(gf, 1, tb.MODE_FAST)
+    check(gs, want, exact=True)
+    check(gf, want, exact=False)
+
+
+def test_one_shot_host_call_matches_reference_semantics():
+    """caar_compute_and_apply_rhs_host == Homme::compute_and_apply_rhs(TestData&) on host arrays."""
+    orc = oracle_for(72)
+    want = orc.init(4)
+    got = want.copy()
+    orc.run(want)
+    tb.compute_and_apply_rhs(got, mode=tb.MODE_STRICT)
+    check(got, want, exact=True)
+
+
+def test_fast_vs_strict_at_scale():
+    """ne=30 (5400 elements, BASELINE configs[2]): the fast kernel against the bit-exact strict kernel on the
+    GPU over the full set, plus a CPU-oracle check of the strict kernel on a slice."""
+    E = 5400
+    s = harness.PortOracle().init(E)
+    a, b = s.copy(), s.copy()
+    run_gpu(a, 2, tb.MODE_STRICT)
+    run_gpu(b, 2, tb.MODE_FAST)
+    for n in harness.MUTATED:
+        assert rel_err(b.arrays[n], a.arrays[n]) <= TOL, n
+    orc = oracle_for(72)
+    s.ctl[0], s.ctl[1] = 5000, 5016
+    orc.run(s, 2, 1)
+    for n in harness.MUTATED:
+        assert np.array_equal(a.arrays[n][5000:5016], s.arrays[n][5000:5016]), n
+
+
+def test_norms_protocol():
+    orc = oracle_for(72)
+    s = orc.init(10)
+    h = tb.Caar(10)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.upload(s.arrays)
+    n0 = h.norms(1)
+    assert np.max(np.abs(n0 - orc.norms(s)) / orc.norms(s)) < 1e-13
+    # sums of squares over disjoint ranges add up (what the ranks all-reduce)
+    tot = h.sumsq(1, 0, 10)
+    parts = h.sumsq(1, 0, 4) + h.sumsq(1, 4, 10)
+    assert np.max(np.abs(tot - parts) / tot) < 1e-14
+    h.close()
+
+
+def test_saxpby():
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 4096, 128 * 256 * 3 + 1):
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        want = x.copy()
+        for _ in range(3):
+            want = 3.0 * want + 5.0 * y
+        tb.saxpby_host(3.0, 5.0, x, y, sweeps=3)
+        assert rel_err(x, want) < 1e-15
+
+
+def test_errors_are_loud():
+    with pytest.raises(tb.CaarError):
+        tb.Caar(0)
+    h = tb.Caar(2)
+    with pytest.raises(tb.CaarError):            # run before set_params
+        h.compute_and_apply_rhs()
+    s = harness.PortOracle().init(2)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.set_control(nete=3)
+    with pytest.raises(tb.CaarError):
+        h.compute_and_apply_rhs()
+    h.set_control(nete=2, np1=7)
+    with pytest.raises(tb.CaarError):
+        h.compute_and_apply_rhs()
+    h.close()

@@ -1,0 +1,115 @@
+// caar_aux.cu — the two small kernels beside the hot path:
+//   * norms: sum of squares of v, T, dp3d at one time level per element, then over elements
+//     (what print_results_2norm reduces, PO/compute_and_apply_rhs.cpp:372-399);
+//   * saxpby: x = a*x + b*y, the reference's bandwidth yardstick (saxpby_test/cxx/common.cpp:3-15).
+#include "caar_device.cuh"
+
+namespace caar {
+namespace {
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double s = 0;
+  if (w == 0) {
+    s = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  }
+  return s;  // valid in warp 0
+}
+
+// one CTA per element: partial[e] = { sum v^2, sum T^2, sum dp^2 } at time level tl
+__global__ void __launch_bounds__(256) norms_partial_kernel(const KernelArgs A, int tl, int nets, double* partial) {
+  __shared__ double red[8];
+  const size_t e = (size_t)(nets + blockIdx.x);
+  const int lf = A.nlev * PTS;
+  const double2* v = reinterpret_cast<const double2*>(A.v + (e * A.ntl + tl) * (size_t)lf * 2);
+  const double* T = A.T + (e * A.ntl + tl) * (size_t)lf;
+  const double* dp = A.dp3d + (e * A.ntl + tl) * (size_t)lf;
+  double sv = 0, sT = 0, sd = 0;
+  for (int n = threadIdx.x; n < lf; n += blockDim.x) {
+    const double2 a = v[n];
+    sv = fma(a.x, a.x, fma(a.y, a.y, sv));
+    const double b = T[n], c = dp[n];
+    sT = fma(b, b, sT);
+    sd = fma(c, c, sd);
+  }
+  sv = block_sum(sv, red);
+  sT = block_sum(sT, red);
+  sd = block_sum(sd, red);
+  if (threadIdx.x == 0) {
+    partial[e * 3 + 0] = sv;
+    partial[e * 3 + 1] = sT;
+    partial[e * 3 + 2] = sd;
+  }
+}
+
+// one CTA: fixed-order reduction of the per-element partials over [nets, nete)
+__global__ void __launch_bounds__(1024) norms_final_kernel(const double* partial, int nets, int nete, double* out3) {
+  __shared__ double red[32];
+  double s[3] = {0, 0, 0};
+  for (int e = nets + threadIdx.x; e < nete; e += blockDim.x) {
+    s[0] += partial[(size_t)e * 3 + 0];
+    s[1] += partial[(size_t)e * 3 + 1];
+    s[2] += partial[(size_t)e * 3 + 2];
+  }
+  for (int c = 0; c < 3; ++c) {
+    const double r = block_sum(s[c], red);
+    if (threadIdx.x == 0) out3[c] = r;
+  }
+}
+
+// grid-stride, 2 doubles per thread per trip (LDG.128/STG.128), x read-modify-write, y read-only
+__global__ void __launch_bounds__(512) saxpby_kernel(double a, double b, double* __restrict__ x,
+                                                      const double* __restrict__ y, size_t n2, size_t n) {
+  double2* x2 = reinterpret_cast<double2*>(x);
+  const double2* y2 = reinterpret_cast<const double2*>(y);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n2; i += 4 * stride) {
+    double2 xv[4], yv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { xv[u] = x2[i + u * stride]; yv[u] = __ldg(y2 + i + u * stride); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      xv[u].x = a * xv[u].x + b * yv[u].x;
+      xv[u].y = a * xv[u].y + b * yv[u].y;
+      x2[i + u * stride] = xv[u];
+    }
+  }
+  for (; i < n2; i += stride) {
+    double2 xv = x2[i];
+    const double2 yv = __ldg(y2 + i);
+    xv.x = a * xv.x + b * yv.x;
+    xv.y = a * xv.y + b * yv.y;
+    x2[i] = xv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) x[n - 1] = a * x[n - 1] + b * y[n - 1];
+}
+
+}  // namespace
+
+cudaError_t launch_norms(const KernelArgs& a, int tl, int nets, int nete, double* partial, double* out3,
+                         cudaStream_t s) {
+  if (nete > nets) norms_partial_kernel<<<nete - nets, 256, 0, s>>>(a, tl, nets, partial);
+  norms_final_kernel<<<1, 1024, 0, s>>>(partial, nets, nete, out3);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const size_t n2 = n / 2;
+  size_t blocks = (n2 + 512 * 4 - 1) / (512 * 4);
+  if (blocks < 1) blocks = 1;
+  const size_t cap = 148 * 4 * 8;  // a few waves of 4 resident CTAs per SM
+  if (blocks > cap) blocks = cap;
+  saxpby_kernel<<<(unsigned)blocks, 512, 0, s>>>(a, b, x, y, n2, n);
+  return cudaGetLastError();
+}
+
+}  // namespace caar

@@ -1,0 +1,56 @@
+// caar_device.cuh — types shared by the CAAR kernels and the C-ABI layer (device layout == host layout).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "caar_b200.h"
+
+namespace caar {
+
+constexpr int NP = 4;
+constexpr int PTS = 16;
+
+// Everything a kernel needs, passed by value (lives in the constant bank of the launch).
+struct KernelArgs {
+  // device pointers, layout of struct Arrays (PO/data_structures.cpp:14-31)
+  const double* D;
+  const double* Dinv;
+  const double* fcor;
+  const double* spheremp;
+  const double* metdet;
+  const double* rmetdet;
+  double* dp3d;
+  double* v;
+  double* T;
+  const double* phis;
+  const double* Qdp;
+  double* eta_dot_dpdn;
+  double* omega_p;
+  double* phi;
+  const double* pecnd;
+  double* vn0;
+  // dims
+  int nelem, nlev, qsize_d, ntl;
+  // Control (element range is LOCAL to this handle)
+  int nets, nete, n0, np1, nm1, qn0;
+  double dt2;
+  // Constants
+  double rrearth, eta_ave_w, Rwv, Rgas, kappa;
+  // HVCoord: only hyai[0]*ps0 enters the path (PO/compute_and_apply_rhs.cpp:82)
+  double hyai0, ps0;
+  // Derivative, row-major Dvv[i][j]
+  double dvv[16];
+};
+
+// launchers (defined in the .cu files); return cudaError_t of the launch
+cudaError_t launch_strict(const KernelArgs& a, cudaStream_t s);
+cudaError_t launch_fused(const KernelArgs& a, cudaStream_t s);
+bool fused_supports(int nlev);
+size_t strict_smem_bytes(int nlev);
+
+cudaError_t launch_norms(const KernelArgs& a, int tl, int nets, int nete, double* partial /*[nelem][3]*/,
+                         double* out3, cudaStream_t s);
+cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t n, cudaStream_t s);
+
+}  // namespace caar
