@@ -165,6 +165,11 @@ int caar_set_stream(caar_handle h, void* cuda_stream);
 int caar_upload(caar_handle h, const caar_arrays* host, unsigned field_mask);
 int caar_download(caar_handle h, const caar_arrays* host, unsigned field_mask);
 
+/* Page-lock / unlock a caller-owned host range in place (cudaHostRegister), so that later
+   caar_upload/caar_download of it are DMA copies at PCIe speed. Optional. */
+int caar_host_register(void* ptr, size_t bytes);
+int caar_host_unregister(void* ptr);
+
 /* Device pointers of the mirrors (for interop, e.g. wrapping in torch tensors, or peer access). */
 int caar_device_arrays(caar_handle h, caar_arrays* dev_out);
 

@@ -1,0 +1,59 @@
+"""The C++ host side on a GPU: the reference's own unmodified driver linked against the shim
+(tinman_sandbox_b200/host/_dropin/pointers_only_b200) and the standalone driver (host/caar_driver) must print
+the norms of the reference driver (tests/golden/pointers_only_stdout.txt)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "tinman_sandbox_b200", "host")
+
+
+def _norm_lines(txt):
+    return [l for l in txt.splitlines() if "||" in l]
+
+
+def _vals(txt):
+    return np.array([float(x) for x in re.findall(r"=\s*([0-9.eE+-]+)", "\n".join(_norm_lines(txt)))])
+
+
+def test_reference_driver_with_shim_strict_is_textually_identical(golden_dir, tmp_path):
+    exe = os.path.join(HOST, "_dropin", "pointers_only_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in driver not built (needs the reference checkout at build time)")
+    want = open(os.path.join(golden_dir, "pointers_only_stdout.txt")).read()
+    out = subprocess.run([exe], capture_output=True, text=True, check=True, cwd=tmp_path,
+                         env=dict(os.environ, CAAR_MODE="strict")).stdout
+    got = "\n".join(l for l in out.splitlines() if "total time" not in l) + "\n"
+    assert got == want
+    # fast mode: same norms to 1e-13, and the dump files have the reference's format
+    out = subprocess.run([exe, "--tinman-num-elems=4", "--tinman-num-exec=2", "--tinman-dump-res=yes"],
+                         capture_output=True, text=True, check=True, cwd=tmp_path).stdout
+    assert len(_vals(out)) == 6
+    for f in ("elem_state_vx.txt", "elem_state_vy.txt", "elem_state_t.txt", "elem_state_dp3d.txt"):
+        lines = open(tmp_path / f).read().splitlines()
+        assert lines[0] == "[0, 0]" and len(lines) == 4 * 72 * 5
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_standalone_driver_prints_reference_norms(mode, golden_dir):
+    exe = os.path.join(HOST, "caar_driver")
+    want = _vals(open(os.path.join(golden_dir, "pointers_only_stdout.txt")).read())
+    out = subprocess.run([exe, f"--caar-mode={mode}"], capture_output=True, text=True, check=True).stdout
+    got = _vals(out)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want) / want) < 1e-13
+    out2 = subprocess.run([exe, f"--caar-mode={mode}", "--caar-resident=no"], capture_output=True, text=True,
+                          check=True).stdout
+    assert np.max(np.abs(_vals(out2) - want) / want) < 1e-13
+
+
+def test_driver_cli_errors():
+    exe = os.path.join(HOST, "caar_driver")
+    assert subprocess.run([exe, "--tinman-num-elems=abc"], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--tinman-dump-res=maybe"], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "--tinman-help"], capture_output=True).returncode == 0

@@ -31,7 +31,7 @@ MODE_FAST, MODE_STRICT = 0, 1
 EXPORTED_SYMBOLS = (
     "caar_last_error", "caar_version", "caar_field_count", "caar_device_count", "caar_create",
     "caar_destroy", "caar_set_params", "caar_set_stream", "caar_upload", "caar_download",
-    "caar_device_arrays", "caar_run", "caar_sync", "caar_launch_count", "caar_timer_start",
+    "caar_device_arrays", "caar_host_register", "caar_host_unregister", "caar_run", "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
     "caar_saxpby_host",
 )
@@ -104,6 +104,8 @@ def load_library():
     lib.caar_upload.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint]
     lib.caar_download.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint]
     lib.caar_device_arrays.argtypes = [C.c_void_p, C.POINTER(Arrays)]
+    lib.caar_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.caar_host_unregister.argtypes = [C.c_void_p]
     lib.caar_run.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.c_int]
     lib.caar_sync.argtypes = [C.c_void_p]
     lib.caar_timer_start.argtypes = [C.c_void_p]

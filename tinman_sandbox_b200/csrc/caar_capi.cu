@@ -227,6 +227,18 @@ static int copy_fields(caar_handle h, const caar_arrays* host, unsigned mask, bo
 int caar_upload(caar_handle h, const caar_arrays* host, unsigned mask) { return copy_fields(h, host, mask, true); }
 int caar_download(caar_handle h, const caar_arrays* host, unsigned mask) { return copy_fields(h, host, mask, false); }
 
+int caar_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(CAAR_ERR_INVALID, "null argument");
+  CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return CAAR_OK;
+}
+
+int caar_host_unregister(void* ptr) {
+  if (!ptr) return fail(CAAR_ERR_INVALID, "null argument");
+  CU_TRY(cudaHostUnregister(ptr));
+  return CAAR_OK;
+}
+
 int caar_device_arrays(caar_handle h, caar_arrays* out) {
   if (!h || !out) return fail(CAAR_ERR_INVALID, "null argument");
   std::memcpy(out, h->dev, sizeof h->dev);

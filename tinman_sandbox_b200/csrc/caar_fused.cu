@@ -1,23 +1,29 @@
-// caar_fused.cu — CAAR_MODE_FAST: the whole of compute_and_apply_rhs for one element in ONE kernel,
-// one HBM pass: every input is read once, every output written once, all 18 reference temporaries
-// (PO/compute_and_apply_rhs.cpp:18-35) live in registers.
+// caar_fused.cu — CAAR_MODE_FAST for nlev = 72 / 128: the whole of compute_and_apply_rhs for one element in
+// ONE kernel and one HBM pass (every input read once, every output written once; all 18 reference
+// temporaries of PO/compute_and_apply_rhs.cpp:18-35 live in registers).
 //
-// Work decomposition ("R4"): one CTA per element, 4*nlev threads. Thread t owns level k = t/4 and GLL
-// row igp = t%4 of that level, i.e. the 4 points jgp=0..3 — 32 contiguous bytes of every scalar
-// level-field and 64 contiguous bytes of the interleaved (u,v) fields, so a warp reads 1 KB / 2 KB
-// contiguous per field. A warp therefore holds 8 consecutive levels.
+// Work decomposition ("R4"): one CTA per element, 4*nlev threads. Thread t owns level k = t/4 and GLL row
+// igp = t%4, i.e. the 4 points jgp = 0..3: 32 contiguous bytes of every scalar level-field, 64 of (u,v).
 //
-//  * sphere operators (PO/sphere_operators.cpp:9-129): the derivative along jgp is thread-local
-//    (16 FMAs against Dvv from the constant bank); the derivative along igp needs the other three rows of
-//    the level, which sit in lanes lane^1, lane^2, lane^3: 3 xor-shuffles per value.
-//  * vertical integrals (pressure PO:76-97, preq_omega_ps PO:314-352, preq_hydrostatic PO:280-312):
-//    warp-shuffle scans across the 8 levels of a warp (lane stride 4: offsets 4, 8, 16), then a carry
-//    across the nlev/8 warps through 3 x (nlev/8) x 16 doubles of shared memory. Two __syncthreads
-//    per element in total.
-//  * divisions: one reciprocal of p serves hkk, ckk, vgrad_p/p and T_v/p (PO:300,333,336,219).
+// Data movement (per element, nlev=72):
+//   * "early" inputs dp3d(n0), v(n0), T(n0), Qdp — needed at once — are LDG.128'd straight into registers;
+//   * "late" inputs derived_vn0, pecnd, derived_omega_p, dp3d(nm1), T(nm1), v(nm1) (72 KB) are fetched by ONE
+//     thread at kernel entry with six TMA bulk copies (cp.async.bulk, SASS UBLKCP) into shared memory and
+//     complete on two mbarriers while the CTA computes: no registers, no LSU, full prefetch distance;
+//   * every output is written IN PLACE over the late input that has the same shape
+//     (vn0->vn0, pecnd->phi, omega_p->omega_p, dp3d(nm1)->dp3d(np1), T(nm1)->T(np1), v(nm1)->v(np1)) and
+//     leaves the SM as six TMA bulk stores: fully coalesced, asynchronous, no per-thread STG.
+//   * the element's 2-D geometry (Dinv*rrearth, D, metdet, rmetdet, fcor, spheremp, phis: 1664 B) sits in
+//     shared memory and is re-read (warp-broadcast) where used, instead of pinning 40 registers.
 //
-// Rounding differs from the reference (FMA contraction, tree-ordered sums, shared reciprocal): results
-// agree to ~1e-14 relative, checked at 1e-12 per field in tests/test_parity_gpu.py.
+// Math:
+//   * sphere operators (PO/sphere_operators.cpp:9-129): derivative along jgp is thread-local (Dvv from the
+//     constant bank), derivative along igp takes the other three rows of the level from lanes lane^1,2,3.
+//   * vertical integrals (PO:76-97, 280-312, 314-352) in scan form: warp-shuffle scans over the 8 levels of
+//     a warp (lane stride 4) + carry over the nlev/8 warps through shared memory; 3 __syncthreads in all.
+//   * one reciprocal of p serves the four divisions by p (PO:219,300,333,336).
+// Rounding differs from the reference by FMA contraction, scan ordering and the shared reciprocal
+// (~1e-15 relative); tests/test_parity_gpu.py holds it to 1e-12 per field.
 #include "caar_device.cuh"
 
 namespace caar {
@@ -25,10 +31,43 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// ---- TMA bulk copy + mbarrier primitives (sm_90+/sm_100a PTX) ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- register tiles -----------------------------------------------------------------------------------
 struct Row {  // the 4 points (jgp = 0..3) of one GLL row of one level
   double x[4];
 };
-
 __device__ __forceinline__ Row ld_row(const double* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
   const double2 b = *reinterpret_cast<const double2*>(p + 2);
@@ -40,8 +79,7 @@ __device__ __forceinline__ void st_row(double* p, const Row& r) {
   *reinterpret_cast<double2*>(p) = make_double2(r.x[0], r.x[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(r.x[2], r.x[3]);
 }
-// interleaved [jgp][2] -> two rows
-__device__ __forceinline__ void ld_row2(const double* p, Row& u, Row& w) {
+__device__ __forceinline__ void ld_row2(const double* p, Row& u, Row& w) {  // interleaved [jgp][2]
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double2 a = *reinterpret_cast<const double2*>(p + 2 * j);
@@ -53,9 +91,14 @@ __device__ __forceinline__ void st_row2(double* p, const Row& u, const Row& w) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p + 2 * j) = make_double2(u.x[j], w.x[j]);
 }
+// shared-memory loads the compiler may not merge/hoist across uses (keeps the geometry out of registers)
+__device__ __forceinline__ double2 lds2(const double* p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)));
+  return v;
+}
 
-// Derivative along igp: out[j] = sum_m Dvv[m][r] * s_m[j], rows m of this level live in lanes lane^x.
-// cx[x] = Dvv[r^x][r].
+// out[j] = sum_m Dvv[m][r] * s_m[j]; rows m of this level live in lanes lane^x; cx[x] = Dvv[r^x][r]
 __device__ __forceinline__ Row deriv_i(const Row& s, const double (&cx)[4]) {
   Row o;
 #pragma unroll
@@ -67,7 +110,7 @@ __device__ __forceinline__ Row deriv_i(const Row& s, const double (&cx)[4]) {
   }
   return o;
 }
-// Derivative along jgp: out[l] = sum_m Dvv[m][l] * s[m] (thread-local; Dvv from the constant bank)
+// out[l] = sum_m Dvv[m][l] * s[m] (thread-local; Dvv from the constant bank)
 __device__ __forceinline__ Row deriv_j(const Row& s, const double* __restrict__ dvv) {
   Row o;
 #pragma unroll
@@ -80,23 +123,21 @@ __device__ __forceinline__ Row deriv_j(const Row& s, const double* __restrict__ 
   return o;
 }
 
-struct Geo {       // per-thread geometry of its GLL row; Dinv pre-scaled by rrearth
-  double di[4][4]; // [jgp][2*a+b] = Dinv[igp][jgp][a][b] * rrearth
-};
-
-// gradient_sphere (PO/sphere_operators.cpp:9-48) for this thread's row
-__device__ __forceinline__ void gradient(const Row& s, const Geo& g, const double (&cx)[4],
+// gradient_sphere (PO/sphere_operators.cpp:9-48) for this thread's row; di = this row's Dinv*rrearth in smem,
+// [jgp][2*a+b]
+__device__ __forceinline__ void gradient(const Row& s, const double* di, const double (&cx)[4],
                                          const double* __restrict__ dvv, Row& g0, Row& g1) {
   const Row a = deriv_i(s, cx);   // v1[igp][jgp]
   const Row b = deriv_j(s, dvv);  // v2[igp][jgp]
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    g0.x[j] = fma(g.di[j][0], a.x[j], g.di[j][2] * b.x[j]);
-    g1.x[j] = fma(g.di[j][1], a.x[j], g.di[j][3] * b.x[j]);
+    const double2 d01 = lds2(di + j * 4), d23 = lds2(di + j * 4 + 2);
+    g0.x[j] = fma(d01.x, a.x[j], d23.x * b.x[j]);
+    g1.x[j] = fma(d01.y, a.x[j], d23.y * b.x[j]);
   }
 }
 
-// inclusive scan over the 8 levels of a warp (same igp => lane stride 4)
+// inclusive scans over the 8 levels of a warp (same igp => lane stride 4)
 __device__ __forceinline__ double scan_down(double v, int lane) {  // towards larger k
 #pragma unroll
   for (int d = 4; d < 32; d <<= 1) {
@@ -115,26 +156,77 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 }
 
 template <int L>
-__global__ void __launch_bounds__(4 * L, (4 * L <= 320) ? 2 : 1) caar_fused_kernel(const KernelArgs A) {
-  constexpr int NW = L / 8;  // warps per element
-  __shared__ double tot[3][NW][16];
+struct Smem {
+  static constexpr int LF = L * PTS;  // doubles per scalar level-field
+  // late inputs, overwritten in place by the outputs of the same shape
+  double vn0[2 * LF];      // derived_vn0           -> derived_vn0
+  double vm1[2 * LF];      // v(nm1)                -> v(np1)
+  double pec[LF];          // derived_pecnd         -> derived_phi
+  double omp[LF];          // derived_omega_p       -> derived_omega_p
+  double dpm[LF];          // dp3d(nm1)             -> dp3d(np1)
+  double Tm1[LF];          // T(nm1)                -> T(np1)
+  double tot[3][L / 8][16];
+  double dinv[64];         // Dinv * rrearth
+  double dmat[64];         // D
+  double met[16], rmet[16], fcor[16], mp[16], phis[16];
+  uint64_t bar[2];
+};
+
+template <int L>
+__global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128) caar_fused_kernel(const KernelArgs A) {
+  constexpr int NW = L / 8;
+  constexpr int LF = L * PTS;
+  constexpr unsigned FB = LF * sizeof(double);  // bytes of one scalar level-field of one element
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem<L>& S = *reinterpret_cast<Smem<L>*>(smem_raw);
 
   const int t = threadIdx.x;
   const int lane = t & 31, w = t >> 5;
   const int r = t & 3;  // igp
   const size_t e = (size_t)(A.nets + blockIdx.x);
-  constexpr size_t lf = (size_t)L * PTS;
-  const size_t off = (size_t)t * 4;  // this thread's 4 points inside a scalar level-field
+  const size_t lf = LF;
+  const int off = t * 4;  // this thread's 4 points inside a scalar level-field
+  const size_t onm1 = (e * A.ntl + A.nm1) * lf, onp1 = (e * A.ntl + A.np1) * lf;
 
-  // ---- issue the n0 loads first
-  const Row dp = ld_row(A.dp3d + (e * A.ntl + A.n0) * lf + off);
+  // ---- kernel entry: one thread starts the TMA prefetch of the late inputs
+  if (t == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    fence_proxy_async();
+    mbar_expect_tx(&S.bar[0], 4 * FB);
+    bulk_g2s(S.vn0, A.vn0 + e * lf * 2, 2 * FB, &S.bar[0]);
+    bulk_g2s(S.dpm, A.dp3d + onm1, FB, &S.bar[0]);
+    bulk_g2s(S.pec, A.pecnd + e * lf, FB, &S.bar[0]);
+    mbar_expect_tx(&S.bar[1], 4 * FB);
+    bulk_g2s(S.omp, A.omega_p + e * lf, FB, &S.bar[1]);
+    bulk_g2s(S.Tm1, A.T + onm1, FB, &S.bar[1]);
+    bulk_g2s(S.vm1, A.v + onm1 * 2, 2 * FB, &S.bar[1]);
+  }
+
+  // ---- early inputs straight to registers
+  const size_t on0 = (e * A.ntl + A.n0) * lf + off;
+  Row dp = ld_row(A.dp3d + on0);
   Row v1, v2;
-  ld_row2(A.v + ((e * A.ntl + A.n0) * lf + off) * 2, v1, v2);
-  const Row T = ld_row(A.T + (e * A.ntl + A.n0) * lf + off);
+  ld_row2(A.v + on0 * 2, v1, v2);
+  Row T = ld_row(A.T + on0);
   Row Tv = T;
-  if (A.qn0 != -1) Tv = ld_row(A.Qdp + ((e * A.qsize_d + 0) * 2 + A.qn0) * lf + off);  // holds Qdp for now
+  if (A.qn0 != -1) Tv = ld_row(A.Qdp + ((e * A.qsize_d + 0) * 2 + A.qn0) * lf + off);  // Qdp for now
 
-  // ---- per-thread constants
+  // ---- stage the element's geometry
+  if (t < 64) {
+    S.dinv[t] = A.Dinv[e * 64 + t] * A.rrearth;
+    S.dmat[t] = A.D[e * 64 + t];
+  } else if (t < 80) {
+    const int q = t - 64;
+    S.met[q] = A.metdet[e * 16 + q];
+    S.rmet[q] = A.rmetdet[e * 16 + q];
+    S.fcor[q] = A.fcor[e * 16 + q];
+  } else if (t < 96) {
+    const int q = t - 80;
+    S.mp[q] = A.spheremp[e * 16 + q];
+    S.phis[q] = A.phis[e * 16 + q];
+  }
+
   double cx[4];  // cx[x] = Dvv[r^x][r]; static indices + selects keep Dvv in the constant bank
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
@@ -144,197 +236,227 @@ __global__ void __launch_bounds__(4 * L, (4 * L <= 320) ? 2 : 1) caar_fused_kern
     if (r == 3) c = A.dvv[(3 ^ x) * 4 + 3];
     cx[x] = c;
   }
-  Geo g;
-  {
-    const double* dinv = A.Dinv + e * 64 + r * 16;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const Row q = ld_row(dinv + j * 4);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) g.di[j][c] = q.x[c] * A.rrearth;
-    }
-  }
-  const Row rmet = ld_row(A.rmetdet + e * 16 + r * 4);
 
   // ---- A: p = hyai0*ps0 + sum_{l<k} dp_l + dp_k/2   (PO:76-97)
-  Row p;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) p.x[j] = scan_down(dp.x[j], lane);
-  if (lane >= 28) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tot[0][w][r * 4 + j] = p.x[j];
-  }
-  __syncthreads();
+  Row rp;
   {
+    Row p;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p.x[j] = scan_down(dp.x[j], lane);
+    if (lane >= 28) st_row(&S.tot[0][w][r * 4], p);
+    __syncthreads();  // (1) tot[0], geometry, mbarrier init visible
     double carry[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ww = 0; ww < NW - 1; ++ww)
       if (ww < w) {
+        const Row c = ld_row(&S.tot[0][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) carry[j] += tot[0][ww][r * 4 + j];
+        for (int j = 0; j < 4; ++j) carry[j] += c.x[j];
       }
     const double ptop = A.hyai0 * A.ps0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) p.x[j] = ptop + ((carry[j] + p.x[j]) - 0.5 * dp.x[j]);
-  }
-  Row rp;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) rp.x[j] = 1.0 / p.x[j];
+    for (int j = 0; j < 4; ++j) {
+      p.x[j] = ptop + ((carry[j] + p.x[j]) - 0.5 * dp.x[j]);
+      rp.x[j] = 1.0 / p.x[j];
+    }
 
-  // ---- B: grad_p, vgrad_p, vdp, vn0, divdp, vort (PO:101-124)
-  Row gp0, gp1;
-  gradient(p, g, cx, A.dvv, gp0, gp1);
-  Row vgp;
+    // ---- B1: grad_p; vgrad_p (PO:103-112); C: T_v (PO:126-156); glnps folded into the v tendencies
+    Row gp0, gp1;
+    gradient(p, S.dinv + r * 16, cx, A.dvv, gp0, gp1);
+    // from here on p is dead; only rp is kept
+    if (A.qn0 != -1) {
+      const double c = A.Rwv / A.Rgas - 1.0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) vgp.x[j] = fma(v1.x[j], gp0.x[j], v2.x[j] * gp1.x[j]);
-
-  Row divdp;
-  {
-    Row u, ww2;
+      for (int j = 0; j < 4; ++j) Tv.x[j] = T.x[j] * fma(c, Tv.x[j] / dp.x[j], 1.0);
+    }
+    // vgp <- v.grad_p ; (gp0,gp1) <- -Rgas*T_v/p * grad_p  (the glnps terms of vtens, PO:219-228)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      u.x[j] = v1.x[j] * dp.x[j];
-      ww2.x[j] = v2.x[j] * dp.x[j];
+      const double vg = fma(v1.x[j], gp0.x[j], v2.x[j] * gp1.x[j]);
+      const double gl = -A.Rgas * (Tv.x[j] * rp.x[j]);
+      gp0.x[j] *= gl;
+      gp1.x[j] *= gl;
+      p.x[j] = vg;  // p now holds vgrad_p
     }
-    {  // derived_vn0 += eta_ave_w * vdp (PO:117-118)
-      double* vn0 = A.vn0 + (e * lf + off) * 2;
-      Row a0, a1;
-      ld_row2(vn0, a0, a1);
+    // ---- vorticity_sphere (PO/sphere_operators.cpp:91-129) -> coriolis/vorticity terms of vtens
+    {
+      Row vc0, vc1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        a0.x[j] = fma(A.eta_ave_w, u.x[j], a0.x[j]);
-        a1.x[j] = fma(A.eta_ave_w, ww2.x[j], a1.x[j]);
+        const double2 d01 = lds2(S.dmat + r * 16 + j * 4), d23 = lds2(S.dmat + r * 16 + j * 4 + 2);
+        vc0.x[j] = fma(d01.x, v1.x[j], d23.x * v2.x[j]);
+        vc1.x[j] = fma(d01.y, v1.x[j], d23.y * v2.x[j]);
       }
-      st_row2(vn0, a0, a1);
+      const Row dvdx = deriv_i(vc1, cx);
+      const Row dudy = deriv_j(vc0, A.dvv);
+      const Row rm = ld_row(S.rmet + r * 4), fc = ld_row(S.fcor + r * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double fv = fma((dvdx.x[j] - dudy.x[j]) * rm.x[j], A.rrearth, fc.x[j]);
+        gp0.x[j] = fma(v2.x[j], fv, gp0.x[j]);   // vtens1 (without grad Ephi)
+        gp1.x[j] = fma(-v1.x[j], fv, gp1.x[j]);  // vtens2 (without grad Ephi)
+      }
     }
-    // divergence_sphere (PO/sphere_operators.cpp:50-89); g.di carries the rrearth factor
-    const Row met = ld_row(A.metdet + e * 16 + r * 4);
-    Row gv0, gv1;
+    Row& vt1 = gp0;
+    Row& vt2 = gp1;
+    Row& vgp = p;
+
+    // ---- grad T -> -v.grad T (PO:200-209)
+    Row ttp;
+    {
+      Row g0, g1;
+      gradient(T, S.dinv + r * 16, cx, A.dvv, g0, g1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ttp.x[j] = -fma(v1.x[j], g0.x[j], v2.x[j] * g1.x[j]);
+    }
+
+    // ---- late inputs, first batch (vn0, dp3d(nm1), pecnd) must have landed
+    mbar_wait(&S.bar[0], 0);
+
+    // ---- B2: vdp, derived_vn0 += eta_ave_w*vdp (PO:114-118), divergence_sphere(vdp) (PO/sphere_operators.cpp:50-89)
+    Row divdp;
+    {
+      Row u, ww2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        u.x[j] = v1.x[j] * dp.x[j];
+        ww2.x[j] = v2.x[j] * dp.x[j];
+      }
+      {
+        Row a0, a1;
+        ld_row2(S.vn0 + off * 2, a0, a1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a0.x[j] = fma(A.eta_ave_w, u.x[j], a0.x[j]);
+          a1.x[j] = fma(A.eta_ave_w, ww2.x[j], a1.x[j]);
+        }
+        st_row2(S.vn0 + off * 2, a0, a1);
+      }
+      const Row met = ld_row(S.met + r * 4);
+      Row gv0, gv1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 d01 = lds2(S.dinv + r * 16 + j * 4), d23 = lds2(S.dinv + r * 16 + j * 4 + 2);
+        gv0.x[j] = met.x[j] * fma(d01.x, u.x[j], d01.y * ww2.x[j]);
+        gv1.x[j] = met.x[j] * fma(d23.x, u.x[j], d23.y * ww2.x[j]);
+      }
+      const Row dudx = deriv_i(gv0, cx);
+      const Row dvdy = deriv_j(gv1, A.dvv);
+      const Row rm = ld_row(S.rmet + r * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) divdp.x[j] = (dudx.x[j] + dvdy.x[j]) * rm.x[j];  // dinv carries rrearth
+    }
+    // dp3d(np1) = spheremp*(dp3d(nm1) - dt2*divdp)  (PO:254), in place over dp3d(nm1)
+    {
+      const Row mp = ld_row(S.mp + r * 4);
+      Row o = ld_row(S.dpm + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o.x[j] = mp.x[j] * fma(-A.dt2, divdp.x[j], o.x[j]);
+      st_row(S.dpm + off, o);
+    }
+    fence_proxy_async();  // vn0 and dp3d(np1) tiles are final: make them visible to the TMA engine
+
+    // ---- kinetic energy + pecnd (PO:196; phi is added after the scan)
+    Row kep;
+    {
+      const Row pec = ld_row(S.pec + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kep.x[j] = fma(0.5, fma(v1.x[j], v1.x[j], v2.x[j] * v2.x[j]), pec.x[j]);
+    }
+    // v1, v2, T are dead from here
+
+    // ---- D+E: the two vertical integrals in scan form
+    //   q_k = Rgas*T_v*dp/p ; phi_k = phis + sum_{l>k} q_l + q_k/2              (PO:280-312)
+    //   omega_k = (vgrad_p - sum_{l<k} divdp_l - divdp_k/2) / p                 (PO:314-352)
+    Row a, ph;
+    {
+      const Row phis = ld_row(S.phis + r * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double q = A.Rgas * Tv.x[j] * (dp.x[j] * rp.x[j]);
+        const double sq = scan_up(q, lane);
+        const double sd = scan_down(divdp.x[j], lane);
+        ph.x[j] = phis.x[j] + (sq - 0.5 * q);
+        a.x[j] = rp.x[j] * (vgp.x[j] - (sd - 0.5 * divdp.x[j]));
+        dp.x[j] = sq;      // reuse: warp totals live in the end lanes
+        divdp.x[j] = sd;
+      }
+      if (lane < 4) st_row(&S.tot[1][w][r * 4], dp);
+      if (lane >= 28) st_row(&S.tot[2][w][r * 4], divdp);
+    }
+    // T tendency with the omega carry factored out: ttens = kappa*T_v*omega - v.gradT, omega = a - rp*carry
+    Row tta, ttb;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      gv0.x[j] = met.x[j] * fma(g.di[j][0], u.x[j], g.di[j][1] * ww2.x[j]);
-      gv1.x[j] = met.x[j] * fma(g.di[j][2], u.x[j], g.di[j][3] * ww2.x[j]);
+      const double kt = A.kappa * Tv.x[j];
+      tta.x[j] = fma(kt, a.x[j], ttp.x[j]);
+      ttb.x[j] = kt * rp.x[j];
     }
-    const Row dudx = deriv_i(gv0, cx);
-    const Row dvdy = deriv_j(gv1, A.dvv);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) divdp.x[j] = (dudx.x[j] + dvdy.x[j]) * rmet.x[j];
-  }
-  Row vort;
-  {  // vorticity_sphere (PO/sphere_operators.cpp:91-129)
-    const double* D = A.D + e * 64 + r * 16;
-    Row vc0, vc1;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const Row d = ld_row(D + j * 4);
-      vc0.x[j] = fma(d.x[0], v1.x[j], d.x[2] * v2.x[j]);
-      vc1.x[j] = fma(d.x[1], v1.x[j], d.x[3] * v2.x[j]);
+    __syncthreads();  // (2) scan totals visible; vn0 / dp3d(np1) tiles complete
+    if (t == 0) {
+      bulk_s2g(A.vn0 + e * lf * 2, S.vn0, 2 * FB);
+      bulk_s2g(A.dp3d + onp1, S.dpm, FB);
+      bulk_commit();
     }
-    const Row dvdx = deriv_i(vc1, cx);
-    const Row dudy = deriv_j(vc0, A.dvv);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) vort.x[j] = (dvdx.x[j] - dudy.x[j]) * rmet.x[j] * A.rrearth;
-  }
-
-  // ---- C: virtual temperature (PO:126-156)
-  if (A.qn0 != -1) {
-    const double c = A.Rwv / A.Rgas - 1.0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Tv.x[j] = T.x[j] * fma(c, Tv.x[j] / dp.x[j], 1.0);
-  }
-
-  // ---- D+E: both vertical integrals in scan form
-  //   q_k = Rgas*T_v*dp/p ; phi_k = phis + sum_{l>k} q_l + q_k/2            (PO:280-312)
-  //   omega_k = (vgrad_p - sum_{l<k} divdp_l - divdp_k/2) / p               (PO:314-352)
-  Row q, sq, sd;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    q.x[j] = A.Rgas * Tv.x[j] * (dp.x[j] * rp.x[j]);
-    sq.x[j] = scan_up(q.x[j], lane);
-    sd.x[j] = scan_down(divdp.x[j], lane);
-  }
-  if (lane < 4) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tot[1][w][r * 4 + j] = sq.x[j];
-  }
-  if (lane >= 28) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tot[2][w][r * 4 + j] = sd.x[j];
-  }
-  __syncthreads();
-  Row omega, phi;
-  {
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ww = 0; ww < NW; ++ww) {
       if (ww > w) {
+        const Row c = ld_row(&S.tot[1][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cq[j] += tot[1][ww][r * 4 + j];
+        for (int j = 0; j < 4; ++j) cq[j] += c.x[j];
       }
       if (ww < w) {
+        const Row c = ld_row(&S.tot[2][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cd[j] += tot[2][ww][r * 4 + j];
+        for (int j = 0; j < 4; ++j) cd[j] += c.x[j];
       }
     }
-    const Row phis = ld_row(A.phis + e * 16 + r * 4);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      phi.x[j] = phis.x[j] + ((cq[j] + sq.x[j]) - 0.5 * q.x[j]);
-      omega.x[j] = rp.x[j] * (vgp.x[j] - ((cd[j] + sd.x[j]) - 0.5 * divdp.x[j]));
-    }
-  }
-  st_row(A.phi + e * lf + off, phi);
-  {  // derived_omega_p += eta_ave_w * omega (PO:173). derived_eta_dot_dpdn += eta_ave_w*0 is value-neutral: skipped.
-    double* op = A.omega_p + e * lf + off;
-    Row a = ld_row(op);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) a.x[j] = fma(A.eta_ave_w, omega.x[j], a.x[j]);
-    st_row(op, a);
-  }
 
-  // ---- G: tendencies (PO:187-234)
-  Row vt1, vt2, tt;
-  {
-    Row gT0, gT1;
-    gradient(T, g, cx, A.dvv, gT0, gT1);
-    const Row pec = ld_row(A.pecnd + e * lf + off);
-    Row Ephi;
+    // ---- late inputs, second batch (omega_p, T(nm1), v(nm1))
+    mbar_wait(&S.bar[1], 0);
+    const Row mp = ld_row(S.mp + r * 4);
+    {  // derived_omega_p += eta_ave_w*omega (PO:173); T(np1) = spheremp*(T(nm1) + dt2*ttens) (PO:253)
+      Row om = ld_row(S.omp + off), Tn = ld_row(S.Tm1 + off);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) Ephi.x[j] = 0.5 * fma(v1.x[j], v1.x[j], v2.x[j] * v2.x[j]) + phi.x[j] + pec.x[j];
-    Row gE0, gE1;
-    gradient(Ephi, g, cx, A.dvv, gE0, gE1);
-    const Row fcor = ld_row(A.fcor + e * 16 + r * 4);
+      for (int j = 0; j < 4; ++j) {
+        const double omega = fma(-rp.x[j], cd[j], a.x[j]);
+        om.x[j] = fma(A.eta_ave_w, omega, om.x[j]);
+        const double tt = fma(-ttb.x[j], cd[j], tta.x[j]);
+        Tn.x[j] = mp.x[j] * fma(A.dt2, tt, Tn.x[j]);
+      }
+      st_row(S.omp + off, om);
+      st_row(S.Tm1 + off, Tn);
+    }
+    // phi (PO:294,303,309) in place over pecnd; Ephi = 0.5|v|^2 + phi + pecnd (PO:196)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const double vgT = fma(v1.x[j], gT0.x[j], v2.x[j] * gT1.x[j]);
-      const double gl = A.Rgas * (Tv.x[j] * rp.x[j]);
-      const double fv = fcor.x[j] + vort.x[j];
-      vt1.x[j] = v2.x[j] * fv - gE0.x[j] - gl * gp0.x[j];
-      vt2.x[j] = -v1.x[j] * fv - gE1.x[j] - gl * gp1.x[j];
-      tt.x[j] = A.kappa * Tv.x[j] * omega.x[j] - vgT;
+      ph.x[j] += cq[j];
+      kep.x[j] += ph.x[j];
+    }
+    st_row(S.pec + off, ph);
+    {  // v(np1) = spheremp*(v(nm1) + dt2*vtens) (PO:251-252), in place over v(nm1)
+      Row g0, g1;
+      gradient(kep, S.dinv + r * 16, cx, A.dvv, g0, g1);
+      Row a0, a1;
+      ld_row2(S.vm1 + off * 2, a0, a1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a0.x[j] = mp.x[j] * fma(A.dt2, vt1.x[j] - g0.x[j], a0.x[j]);
+        a1.x[j] = mp.x[j] * fma(A.dt2, vt2.x[j] - g1.x[j], a1.x[j]);
+      }
+      st_row2(S.vm1 + off * 2, a0, a1);
     }
   }
-
-  // ---- H: apply (PO:236-257). Each thread reads nm1 and writes np1 only at its own points, after all of
-  // its n0 reads: time levels may alias.
-  {
-    const Row mp = ld_row(A.spheremp + e * 16 + r * 4);
-    const size_t onm1 = (e * A.ntl + A.nm1) * lf + off, onp1 = (e * A.ntl + A.np1) * lf + off;
-    Row a0, a1;
-    ld_row2(A.v + onm1 * 2, a0, a1);
-    const Row Tm = ld_row(A.T + onm1);
-    const Row dpm = ld_row(A.dp3d + onm1);
-    Row oT, odp;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      a0.x[j] = mp.x[j] * fma(A.dt2, vt1.x[j], a0.x[j]);
-      a1.x[j] = mp.x[j] * fma(A.dt2, vt2.x[j], a1.x[j]);
-      oT.x[j] = mp.x[j] * fma(A.dt2, tt.x[j], Tm.x[j]);
-      odp.x[j] = mp.x[j] * fma(-A.dt2, divdp.x[j], dpm.x[j]);
-    }
-    st_row2(A.v + onp1 * 2, a0, a1);
-    st_row(A.T + onp1, oT);
-    st_row(A.dp3d + onp1, odp);
+  fence_proxy_async();
+  __syncthreads();  // (3) all output tiles complete
+  if (t == 0) {
+    bulk_s2g(A.omega_p + e * lf, S.omp, FB);
+    bulk_s2g(A.T + onp1, S.Tm1, FB);
+    bulk_s2g(A.phi + e * lf, S.pec, FB);
+    bulk_s2g(A.v + onp1 * 2, S.vm1, 2 * FB);
+    bulk_commit();
+    bulk_wait_read_all();  // shared memory must stay alive until the TMA engine has read it
   }
 }
 
@@ -342,24 +464,24 @@ template <int L>
 cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   const int n = a.nete - a.nets;
   if (n <= 0) return cudaSuccess;
-  caar_fused_kernel<L><<<n, 4 * L, 0, s>>>(a);
+  // per device (function attributes are per context): cheap enough to set on every launch
+  cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem<L>));
+  if (e != cudaSuccess) return e;
+  caar_fused_kernel<L><<<n, 4 * L, sizeof(Smem<L>), s>>>(a);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-bool fused_supports(int nlev) { return nlev == 72 || nlev == 128 || nlev == 64 || nlev == 32 || nlev == 8 || nlev == 16; }
+bool fused_supports(int nlev) { return nlev == 72 || nlev == 128 || fused_ldg_supports(nlev); }
 
 cudaError_t launch_fused(const KernelArgs& a, cudaStream_t s) {
   switch (a.nlev) {
-    case 8: return launch_L<8>(a, s);
-    case 16: return launch_L<16>(a, s);
-    case 32: return launch_L<32>(a, s);
-    case 64: return launch_L<64>(a, s);
     case 72: return launch_L<72>(a, s);
     case 128: return launch_L<128>(a, s);
   }
-  return cudaErrorInvalidValue;
+  return launch_fused_ldg(a, s);
 }
 
 }  // namespace caar
