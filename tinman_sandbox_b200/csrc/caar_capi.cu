@@ -59,6 +59,7 @@ struct caar_handle_s {
   double* out3_host;  // [3] pinned
   cudaEvent_t ev0, ev1;
   long long launches;
+  caar::TmaMaps* tma;  // TMA descriptors of the device mirrors (nlev with a TMA-pipelined kernel only)
 };
 
 static_assert(sizeof(caar_arrays) == CAAR_NUM_FIELDS * sizeof(double*), "caar_arrays must be 16 pointers");
@@ -104,6 +105,7 @@ caar::KernelArgs make_args(const caar_handle_s* h, const caar_control* ctl) {
   a.rrearth = h->c.rrearth; a.eta_ave_w = h->c.eta_ave_w; a.Rwv = h->c.Rwater_vapor; a.Rgas = h->c.Rgas;
   a.kappa = h->c.kappa; a.hyai0 = h->hyai0; a.ps0 = h->ps0;
   for (int i = 0; i < 16; ++i) a.dvv[i] = h->dvv[i];
+  a.tma = h->tma;
   return a;
 }
 
@@ -171,6 +173,14 @@ int caar_create(caar_handle* out, const caar_dims* dims, int device) {
     return code;
   }
   h->stream = h->own_stream;
+  if (dims->nlev == 72 || dims->nlev == 128) {
+    h->tma = new (std::nothrow) caar::TmaMaps();
+    char msg[256] = "host allocation failed";
+    if (!h->tma || caar::build_tma_maps(h->tma, make_args(h, nullptr), msg, sizeof msg)) {
+      caar_destroy(h);
+      return fail(CAAR_ERR_CUDA, "caar_create: %s", msg);
+    }
+  }
   *out = h;
   return CAAR_OK;
 }
@@ -187,6 +197,7 @@ int caar_destroy(caar_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h->tma;
   delete h;
   return CAAR_OK;
 }

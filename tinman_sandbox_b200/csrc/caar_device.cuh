@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "caar_b200.h"
@@ -41,7 +42,17 @@ struct KernelArgs {
   double hyai0, ps0;
   // Derivative, row-major Dvv[i][j]
   double dvv[16];
+  // host pointer to the handle's TMA descriptors (TmaMaps), or null; only the launcher reads it
+  const void* tma;
 };
+
+// TMA tensor maps over the level-field arrays viewed as 2-D [rows of 128 B][16 doubles], box = one
+// element's slice, SWIZZLE_128B (conflict-free shared-memory tiles). Built once per handle.
+struct alignas(64) TmaMaps {
+  CUtensorMap dp3d, T, v, vn0, pecnd, omega_p, phi;
+};
+// returns 0 on success; on failure writes a message
+int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen);
 
 // launchers (defined in the .cu files); return cudaError_t of the launch
 cudaError_t launch_strict(const KernelArgs& a, cudaStream_t s);

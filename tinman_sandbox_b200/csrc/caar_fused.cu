@@ -24,6 +24,8 @@
 //   * one reciprocal of p serves the four divisions by p (PO:219,300,333,336).
 // Rounding differs from the reference by FMA contraction, scan ordering and the shared reciprocal
 // (~1e-15 relative); tests/test_parity_gpu.py holds it to 1e-12 per field.
+#include <cstdio>
+
 #include "caar_device.cuh"
 
 namespace caar {
@@ -40,11 +42,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// 2-D tiled TMA load: rows [row, row+box) x 16 doubles of the array behind `map` -> swizzled smem tile
+__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* map, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(0), "r"(row), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   const uint32_t addr = smem_u32(bar);
@@ -57,12 +61,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+// 2-D tiled TMA store: swizzled smem tile -> rows [row, row+box) of the array behind `map`
+__device__ __forceinline__ void tma_store(const CUtensorMap* map, int row, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0),
+               "r"(row), "r"(smem_u32(src))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// 1/x to ~1 ulp: hardware 20-bit seed + two Newton steps (x is a positive, normal pressure / thickness)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
 
 // ---- register tiles -----------------------------------------------------------------------------------
 struct Row {  // the 4 points (jgp = 0..3) of one GLL row of one level
@@ -91,6 +106,38 @@ __device__ __forceinline__ void st_row2(double* p, const Row& u, const Row& w) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p + 2 * j) = make_double2(u.x[j], w.x[j]);
 }
+// Tiles written by TMA with SWIZZLE_128B: inside every 1024-byte block the 16-byte chunk index (address bits
+// 4-6) is XORed with the 128-byte row index (bits 7-9). `sw` is this thread's byte offset of its first chunk;
+// its other chunks are sw ^ 16, sw ^ 32, sw ^ 48. The 8 lanes of a quarter-warp hit 8 different chunk columns:
+// conflict-free 128-bit accesses.
+__device__ __forceinline__ Row ld_tile(const double* tile, uint32_t sw) {
+  const char* b = reinterpret_cast<const char*>(tile);
+  const double2 a = *reinterpret_cast<const double2*>(b + sw);
+  const double2 c = *reinterpret_cast<const double2*>(b + (sw ^ 16));
+  Row r;
+  r.x[0] = a.x; r.x[1] = a.y; r.x[2] = c.x; r.x[3] = c.y;
+  return r;
+}
+__device__ __forceinline__ void st_tile(double* tile, uint32_t sw, const Row& r) {
+  char* b = reinterpret_cast<char*>(tile);
+  *reinterpret_cast<double2*>(b + sw) = make_double2(r.x[0], r.x[1]);
+  *reinterpret_cast<double2*>(b + (sw ^ 16)) = make_double2(r.x[2], r.x[3]);
+}
+__device__ __forceinline__ void ld_tile2(const double* tile, uint32_t sw, Row& u, Row& w) {  // interleaved (u,v)
+  const char* b = reinterpret_cast<const char*>(tile);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double2 a = *reinterpret_cast<const double2*>(b + (sw ^ (j << 4)));
+    u.x[j] = a.x;
+    w.x[j] = a.y;
+  }
+}
+__device__ __forceinline__ void st_tile2(double* tile, uint32_t sw, const Row& u, const Row& w) {
+  char* b = reinterpret_cast<char*>(tile);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(b + (sw ^ (j << 4))) = make_double2(u.x[j], w.x[j]);
+}
+
 // shared-memory loads the compiler may not merge/hoist across uses (keeps the geometry out of registers)
 __device__ __forceinline__ double2 lds2(const double* p) {
   double2 v;
@@ -155,6 +202,10 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
   return v;
 }
 
+#ifndef CAAR_REGS_SMALL
+#define CAAR_REGS_SMALL 96  // 2 CTAs of 9 warps per SM = 5 warps on the fullest SMSP: 16384/(5*32) = 102 -> 96
+#endif
+
 template <int L>
 struct Smem {
   static constexpr int LF = L * PTS;  // doubles per scalar level-field
@@ -166,19 +217,23 @@ struct Smem {
   double dpm[LF];          // dp3d(nm1)             -> dp3d(np1)
   double Tm1[LF];          // T(nm1)                -> T(np1)
   double tot[3][L / 8][16];
-  double dinv[64];         // Dinv * rrearth
-  double dmat[64];         // D
+  // 2x2 tensors: [igp] stride GS = 20 doubles (160 B) instead of 16 so that the four rows read by the
+  // four igp-lanes of a level fall into different banks (conflict-free 128-bit broadcast loads)
+  double dinv[4 * 20];     // Dinv * rrearth, [igp][jgp][2][2]
+  double dmat[4 * 20];     // D
   double met[16], rmet[16], fcor[16], mp[16], phis[16];
   uint64_t bar[2];
 };
 
 template <int L>
-__global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128) caar_fused_kernel(const KernelArgs A) {
+__global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_SMALL : 128) caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ TmaMaps M) {
   constexpr int NW = L / 8;
   constexpr int LF = L * PTS;
+  constexpr int GS = 20;  // padded igp stride of the 2x2 tensors in shared memory
   constexpr unsigned FB = LF * sizeof(double);  // bytes of one scalar level-field of one element
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem<L>& S = *reinterpret_cast<Smem<L>*>(smem_raw);
+  extern __shared__ unsigned char smem_raw[];
+  // swizzled TMA tiles need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
+  Smem<L>& S = *reinterpret_cast<Smem<L>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int t = threadIdx.x;
   const int lane = t & 31, w = t >> 5;
@@ -186,7 +241,11 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
   const size_t e = (size_t)(A.nets + blockIdx.x);
   const size_t lf = LF;
   const int off = t * 4;  // this thread's 4 points inside a scalar level-field
-  const size_t onm1 = (e * A.ntl + A.nm1) * lf, onp1 = (e * A.ntl + A.np1) * lf;
+  // this thread's first 16-byte chunk inside a swizzled scalar tile (row = level) / (u,v) tile (row = t/2)
+  const uint32_t sw1 = (uint32_t)(t >> 2) * 128u + ((uint32_t)((2 * r) ^ ((t >> 2) & 7)) << 4);
+  const uint32_t sw2 = (uint32_t)(t >> 1) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((t >> 1) & 7)) << 4);
+  const int ie = A.nets + (int)blockIdx.x;
+  const int row_nm1 = (ie * A.ntl + A.nm1) * L, row_np1 = (ie * A.ntl + A.np1) * L;
 
   // ---- kernel entry: one thread starts the TMA prefetch of the late inputs
   if (t == 0) {
@@ -194,13 +253,13 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
     mbar_init(&S.bar[1], 1);
     fence_proxy_async();
     mbar_expect_tx(&S.bar[0], 4 * FB);
-    bulk_g2s(S.vn0, A.vn0 + e * lf * 2, 2 * FB, &S.bar[0]);
-    bulk_g2s(S.dpm, A.dp3d + onm1, FB, &S.bar[0]);
-    bulk_g2s(S.pec, A.pecnd + e * lf, FB, &S.bar[0]);
+    tma_load(S.vn0, &M.vn0, ie * 2 * L, &S.bar[0]);
+    tma_load(S.dpm, &M.dp3d, row_nm1, &S.bar[0]);
+    tma_load(S.pec, &M.pecnd, ie * L, &S.bar[0]);
     mbar_expect_tx(&S.bar[1], 4 * FB);
-    bulk_g2s(S.omp, A.omega_p + e * lf, FB, &S.bar[1]);
-    bulk_g2s(S.Tm1, A.T + onm1, FB, &S.bar[1]);
-    bulk_g2s(S.vm1, A.v + onm1 * 2, 2 * FB, &S.bar[1]);
+    tma_load(S.omp, &M.omega_p, ie * L, &S.bar[1]);
+    tma_load(S.Tm1, &M.T, row_nm1, &S.bar[1]);
+    tma_load(S.vm1, &M.v, row_nm1 * 2, &S.bar[1]);
   }
 
   // ---- early inputs straight to registers
@@ -214,8 +273,8 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
 
   // ---- stage the element's geometry
   if (t < 64) {
-    S.dinv[t] = A.Dinv[e * 64 + t] * A.rrearth;
-    S.dmat[t] = A.D[e * 64 + t];
+    S.dinv[(t >> 4) * GS + (t & 15)] = A.Dinv[e * 64 + t] * A.rrearth;
+    S.dmat[(t >> 4) * GS + (t & 15)] = A.D[e * 64 + t];
   } else if (t < 80) {
     const int q = t - 64;
     S.met[q] = A.metdet[e * 16 + q];
@@ -257,17 +316,17 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       p.x[j] = ptop + ((carry[j] + p.x[j]) - 0.5 * dp.x[j]);
-      rp.x[j] = 1.0 / p.x[j];
+      rp.x[j] = fast_rcp(p.x[j]);
     }
 
     // ---- B1: grad_p; vgrad_p (PO:103-112); C: T_v (PO:126-156); glnps folded into the v tendencies
     Row gp0, gp1;
-    gradient(p, S.dinv + r * 16, cx, A.dvv, gp0, gp1);
+    gradient(p, S.dinv + r * GS, cx, A.dvv, gp0, gp1);
     // from here on p is dead; only rp is kept
     if (A.qn0 != -1) {
       const double c = A.Rwv / A.Rgas - 1.0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Tv.x[j] = T.x[j] * fma(c, Tv.x[j] / dp.x[j], 1.0);
+      for (int j = 0; j < 4; ++j) Tv.x[j] = T.x[j] * fma(c, Tv.x[j] * fast_rcp(dp.x[j]), 1.0);
     }
     // vgp <- v.grad_p ; (gp0,gp1) <- -Rgas*T_v/p * grad_p  (the glnps terms of vtens, PO:219-228)
 #pragma unroll
@@ -283,7 +342,7 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
       Row vc0, vc1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double2 d01 = lds2(S.dmat + r * 16 + j * 4), d23 = lds2(S.dmat + r * 16 + j * 4 + 2);
+        const double2 d01 = lds2(S.dmat + r * GS + j * 4), d23 = lds2(S.dmat + r * GS + j * 4 + 2);
         vc0.x[j] = fma(d01.x, v1.x[j], d23.x * v2.x[j]);
         vc1.x[j] = fma(d01.y, v1.x[j], d23.y * v2.x[j]);
       }
@@ -305,7 +364,7 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
     Row ttp;
     {
       Row g0, g1;
-      gradient(T, S.dinv + r * 16, cx, A.dvv, g0, g1);
+      gradient(T, S.dinv + r * GS, cx, A.dvv, g0, g1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) ttp.x[j] = -fma(v1.x[j], g0.x[j], v2.x[j] * g1.x[j]);
     }
@@ -324,19 +383,19 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
       }
       {
         Row a0, a1;
-        ld_row2(S.vn0 + off * 2, a0, a1);
+        ld_tile2(S.vn0, sw2, a0, a1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           a0.x[j] = fma(A.eta_ave_w, u.x[j], a0.x[j]);
           a1.x[j] = fma(A.eta_ave_w, ww2.x[j], a1.x[j]);
         }
-        st_row2(S.vn0 + off * 2, a0, a1);
+        st_tile2(S.vn0, sw2, a0, a1);
       }
       const Row met = ld_row(S.met + r * 4);
       Row gv0, gv1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double2 d01 = lds2(S.dinv + r * 16 + j * 4), d23 = lds2(S.dinv + r * 16 + j * 4 + 2);
+        const double2 d01 = lds2(S.dinv + r * GS + j * 4), d23 = lds2(S.dinv + r * GS + j * 4 + 2);
         gv0.x[j] = met.x[j] * fma(d01.x, u.x[j], d01.y * ww2.x[j]);
         gv1.x[j] = met.x[j] * fma(d23.x, u.x[j], d23.y * ww2.x[j]);
       }
@@ -349,17 +408,17 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
     // dp3d(np1) = spheremp*(dp3d(nm1) - dt2*divdp)  (PO:254), in place over dp3d(nm1)
     {
       const Row mp = ld_row(S.mp + r * 4);
-      Row o = ld_row(S.dpm + off);
+      Row o = ld_tile(S.dpm, sw1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o.x[j] = mp.x[j] * fma(-A.dt2, divdp.x[j], o.x[j]);
-      st_row(S.dpm + off, o);
+      st_tile(S.dpm, sw1, o);
     }
     fence_proxy_async();  // vn0 and dp3d(np1) tiles are final: make them visible to the TMA engine
 
     // ---- kinetic energy + pecnd (PO:196; phi is added after the scan)
     Row kep;
     {
-      const Row pec = ld_row(S.pec + off);
+      const Row pec = ld_tile(S.pec, sw1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) kep.x[j] = fma(0.5, fma(v1.x[j], v1.x[j], v2.x[j] * v2.x[j]), pec.x[j]);
     }
@@ -394,8 +453,8 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
     }
     __syncthreads();  // (2) scan totals visible; vn0 / dp3d(np1) tiles complete
     if (t == 0) {
-      bulk_s2g(A.vn0 + e * lf * 2, S.vn0, 2 * FB);
-      bulk_s2g(A.dp3d + onp1, S.dpm, FB);
+      tma_store(&M.vn0, ie * 2 * L, S.vn0);
+      tma_store(&M.dp3d, row_np1, S.dpm);
       bulk_commit();
     }
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
@@ -417,7 +476,7 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
     mbar_wait(&S.bar[1], 0);
     const Row mp = ld_row(S.mp + r * 4);
     {  // derived_omega_p += eta_ave_w*omega (PO:173); T(np1) = spheremp*(T(nm1) + dt2*ttens) (PO:253)
-      Row om = ld_row(S.omp + off), Tn = ld_row(S.Tm1 + off);
+      Row om = ld_tile(S.omp, sw1), Tn = ld_tile(S.Tm1, sw1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double omega = fma(-rp.x[j], cd[j], a.x[j]);
@@ -425,8 +484,8 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
         const double tt = fma(-ttb.x[j], cd[j], tta.x[j]);
         Tn.x[j] = mp.x[j] * fma(A.dt2, tt, Tn.x[j]);
       }
-      st_row(S.omp + off, om);
-      st_row(S.Tm1 + off, Tn);
+      st_tile(S.omp, sw1, om);
+      st_tile(S.Tm1, sw1, Tn);
     }
     // phi (PO:294,303,309) in place over pecnd; Ephi = 0.5|v|^2 + phi + pecnd (PO:196)
 #pragma unroll
@@ -434,27 +493,27 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? 112 : 128)
       ph.x[j] += cq[j];
       kep.x[j] += ph.x[j];
     }
-    st_row(S.pec + off, ph);
+    st_tile(S.pec, sw1, ph);
     {  // v(np1) = spheremp*(v(nm1) + dt2*vtens) (PO:251-252), in place over v(nm1)
       Row g0, g1;
-      gradient(kep, S.dinv + r * 16, cx, A.dvv, g0, g1);
+      gradient(kep, S.dinv + r * GS, cx, A.dvv, g0, g1);
       Row a0, a1;
-      ld_row2(S.vm1 + off * 2, a0, a1);
+      ld_tile2(S.vm1, sw2, a0, a1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         a0.x[j] = mp.x[j] * fma(A.dt2, vt1.x[j] - g0.x[j], a0.x[j]);
         a1.x[j] = mp.x[j] * fma(A.dt2, vt2.x[j] - g1.x[j], a1.x[j]);
       }
-      st_row2(S.vm1 + off * 2, a0, a1);
+      st_tile2(S.vm1, sw2, a0, a1);
     }
   }
   fence_proxy_async();
   __syncthreads();  // (3) all output tiles complete
   if (t == 0) {
-    bulk_s2g(A.omega_p + e * lf, S.omp, FB);
-    bulk_s2g(A.T + onp1, S.Tm1, FB);
-    bulk_s2g(A.phi + e * lf, S.pec, FB);
-    bulk_s2g(A.v + onp1 * 2, S.vm1, 2 * FB);
+    tma_store(&M.omega_p, ie * L, S.omp);
+    tma_store(&M.T, row_np1, S.Tm1);
+    tma_store(&M.phi, ie * L, S.pec);
+    tma_store(&M.v, row_np1 * 2, S.vm1);
     bulk_commit();
     bulk_wait_read_all();  // shared memory must stay alive until the TMA engine has read it
   }
@@ -466,13 +525,62 @@ cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   // per device (function attributes are per context): cheap enough to set on every launch
   cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(Smem<L>));
+                                       (int)sizeof(Smem<L>) + 1024);
   if (e != cudaSuccess) return e;
-  caar_fused_kernel<L><<<n, 4 * L, sizeof(Smem<L>), s>>>(a);
+  // ask for the largest shared-memory carveout so that two 79 KB CTAs are resident per SM
+  e = cudaFuncSetAttribute(caar_fused_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  if (!a.tma) return cudaErrorInvalidValue;
+  caar_fused_kernel<L><<<n, 4 * L, sizeof(Smem<L>) + 1024, s>>>(a, *static_cast<const TmaMaps*>(a.tma));
   return cudaGetLastError();
 }
 
 }  // namespace
+
+int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) {
+  typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (ce != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(ce));
+    return 1;
+  }
+  const encode_t encode = reinterpret_cast<encode_t>(fn);
+  const cuuint64_t E = (cuuint64_t)a.nelem, L = (cuuint64_t)a.nlev, ntl = (cuuint64_t)a.ntl;
+  struct Spec { CUtensorMap* m; const void* base; cuuint64_t rows; cuuint32_t box; const char* name; };
+  const Spec specs[7] = {
+      {&out->dp3d, a.dp3d, E * ntl * L, (cuuint32_t)L, "dp3d"},
+      {&out->T, a.T, E * ntl * L, (cuuint32_t)L, "T"},
+      {&out->v, a.v, E * ntl * L * 2, (cuuint32_t)(2 * L), "v"},
+      {&out->vn0, a.vn0, E * L * 2, (cuuint32_t)(2 * L), "vn0"},
+      {&out->pecnd, a.pecnd, E * L, (cuuint32_t)L, "pecnd"},
+      {&out->omega_p, a.omega_p, E * L, (cuuint32_t)L, "omega_p"},
+      {&out->phi, a.phi, E * L, (cuuint32_t)L, "phi"},
+  };
+  for (const Spec& sp : specs) {
+    const cuuint64_t gdim[2] = {16, sp.rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {16, sp.box};
+    const cuuint32_t estride[2] = {1, 1};
+    if (sp.box > 256 || sp.rows >= (1ull << 31)) {
+      snprintf(err, errlen, "tensor map %s: box %u rows / %llu rows out of range", sp.name, sp.box,
+               (unsigned long long)sp.rows);
+      return 1;
+    }
+    const CUresult r = encode(sp.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(sp.base), gdim, gstride, box,
+                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(err, errlen, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", sp.name, (int)r);
+      return 1;
+    }
+  }
+  return 0;
+}
 
 bool fused_supports(int nlev) { return nlev == 72 || nlev == 128 || fused_ldg_supports(nlev); }
 
