@@ -44,6 +44,8 @@ struct KernelArgs {
   double dvv[16];
   // host pointer to the handle's TMA descriptors (TmaMaps), or null; only the launcher reads it
   const void* tma;
+  // L2 prefetch distance in elements (0 = off): CTA e prefetches the early inputs of element e + pf_dist
+  int pf_dist;
 };
 
 // TMA tensor maps over the level-field arrays viewed as 2-D [rows of 128 B][16 doubles], box = one

@@ -25,6 +25,7 @@
 // Rounding differs from the reference by FMA contraction, scan ordering and the shared reciprocal
 // (~1e-15 relative); tests/test_parity_gpu.py holds it to 1e-12 per field.
 #include <cstdio>
+#include <cstdlib>
 
 #include "caar_device.cuh"
 
@@ -66,6 +67,9 @@ __device__ __forceinline__ void tma_store(const CUtensorMap* map, int row, const
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0),
                "r"(row), "r"(smem_u32(src))
                : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -260,6 +264,16 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
     tma_load(S.omp, &M.omega_p, ie * L, &S.bar[1]);
     tma_load(S.Tm1, &M.T, row_nm1, &S.bar[1]);
     tma_load(S.vm1, &M.v, row_nm1 * 2, &S.bar[1]);
+    // pull the early inputs of a later element (the one expected to run next on this SM slot) into L2, so
+    // that its kernel-start loads see L2 latency instead of DRAM latency
+    const int pe = ie + A.pf_dist;
+    if (A.pf_dist > 0 && pe < A.nete) {
+      const size_t pn0 = ((size_t)pe * A.ntl + A.n0) * lf;
+      prefetch_l2(A.dp3d + pn0, FB);
+      prefetch_l2(A.v + pn0 * 2, 2 * FB);
+      prefetch_l2(A.T + pn0, FB);
+      if (A.qn0 != -1) prefetch_l2(A.Qdp + (((size_t)pe * A.qsize_d + 0) * 2 + A.qn0) * lf, FB);
+    }
   }
 
   // ---- early inputs straight to registers
@@ -584,7 +598,14 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
 
 bool fused_supports(int nlev) { return nlev == 72 || nlev == 128 || fused_ldg_supports(nlev); }
 
-cudaError_t launch_fused(const KernelArgs& a, cudaStream_t s) {
+cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
+  KernelArgs a = a0;
+  static const int pf_env = [] {
+    const char* v = getenv("CAAR_PF_DIST");
+    return v ? atoi(v) : -1;
+  }();
+  // default distance 148 elements (one CTA per SM ahead): best of a 0/74/148/296/592 sweep at ne=120
+  a.pf_dist = pf_env >= 0 ? pf_env : 148;
   switch (a.nlev) {
     case 72: return launch_L<72>(a, s);
     case 128: return launch_L<128>(a, s);
