@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
     tma_load(S.omp, &M.omega_p, ie * L, &S.bar[1]);
     tma_load(S.Tm1, &M.T, row_nm1, &S.bar[1]);
     tma_load(S.vm1, &M.v, row_nm1 * 2, &S.bar[1]);
-    // pull the early inputs of a later element (the one expected to run next on this SM slot) into L2, so
+    // pull the early inputs and the geometry of a later element (the one expected to run next on this SM slot) into L2, so
     // that its kernel-start loads see L2 latency instead of DRAM latency
     const int pe = ie + A.pf_dist;
     if (A.pf_dist > 0 && pe < A.nete) {
@@ -273,6 +273,13 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
       prefetch_l2(A.v + pn0 * 2, 2 * FB);
       prefetch_l2(A.T + pn0, FB);
       if (A.qn0 != -1) prefetch_l2(A.Qdp + (((size_t)pe * A.qsize_d + 0) * 2 + A.qn0) * lf, FB);
+      prefetch_l2(A.Dinv + (size_t)pe * 64, 512);
+      prefetch_l2(A.D + (size_t)pe * 64, 512);
+      prefetch_l2(A.metdet + (size_t)pe * 16, 128);
+      prefetch_l2(A.rmetdet + (size_t)pe * 16, 128);
+      prefetch_l2(A.fcor + (size_t)pe * 16, 128);
+      prefetch_l2(A.spheremp + (size_t)pe * 16, 128);
+      prefetch_l2(A.phis + (size_t)pe * 16, 128);
     }
   }
 
