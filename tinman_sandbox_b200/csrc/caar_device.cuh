@@ -51,7 +51,7 @@ struct KernelArgs {
 // TMA tensor maps over the level-field arrays viewed as 2-D [rows of 128 B][16 doubles], box = one
 // element's slice, SWIZZLE_128B (conflict-free shared-memory tiles). Built once per handle.
 struct alignas(64) TmaMaps {
-  CUtensorMap dp3d, T, v, vn0, pecnd, omega_p, phi;
+  CUtensorMap dp3d, T, v, vn0, pecnd, omega_p, phi, Qdp;
 };
 // returns 0 on success; on failure writes a message
 int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen);

@@ -220,13 +220,15 @@ struct Smem {
   double omp[LF];          // derived_omega_p       -> derived_omega_p
   double dpm[LF];          // dp3d(nm1)             -> dp3d(np1)
   double Tm1[LF];          // T(nm1)                -> T(np1)
+  double Tn0[LF];          // T(n0)   (input only: keeps 8 registers free during the grad-p peak)
+  double Qd[LF];           // Qdp     (input only)
   double tot[3][L / 8][16];
   // 2x2 tensors: [igp] stride GS = 20 doubles (160 B) instead of 16 so that the four rows read by the
   // four igp-lanes of a level fall into different banks (conflict-free 128-bit broadcast loads)
   double dinv[4 * 20];     // Dinv * rrearth, [igp][jgp][2][2]
   double dmat[4 * 20];     // D
   double met[16], rmet[16], fcor[16], mp[16], phis[16];
-  uint64_t bar[2];
+  uint64_t bar[3];
 };
 
 template <int L>
@@ -255,7 +257,11 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
   if (t == 0) {
     mbar_init(&S.bar[0], 1);
     mbar_init(&S.bar[1], 1);
+    mbar_init(&S.bar[2], 1);
     fence_proxy_async();
+    mbar_expect_tx(&S.bar[2], (A.qn0 != -1 ? 2 : 1) * FB);
+    tma_load(S.Tn0, &M.T, (ie * A.ntl + A.n0) * L, &S.bar[2]);
+    if (A.qn0 != -1) tma_load(S.Qd, &M.Qdp, ((ie * A.qsize_d + 0) * 2 + A.qn0) * L, &S.bar[2]);
     mbar_expect_tx(&S.bar[0], 4 * FB);
     tma_load(S.vn0, &M.vn0, ie * 2 * L, &S.bar[0]);
     tma_load(S.dpm, &M.dp3d, row_nm1, &S.bar[0]);
@@ -288,9 +294,6 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
   Row dp = ld_row(A.dp3d + on0);
   Row v1, v2;
   ld_row2(A.v + on0 * 2, v1, v2);
-  Row T = ld_row(A.T + on0);
-  Row Tv = T;
-  if (A.qn0 != -1) Tv = ld_row(A.Qdp + ((e * A.qsize_d + 0) * 2 + A.qn0) * lf + off);  // Qdp for now
 
   // ---- stage the element's geometry
   if (t < 64) {
@@ -344,10 +347,13 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
     Row gp0, gp1;
     gradient(p, S.dinv + r * GS, cx, A.dvv, gp0, gp1);
     // from here on p is dead; only rp is kept
+    mbar_wait(&S.bar[2], 0);  // T(n0), Qdp tiles
+    Row Tv = ld_tile(S.Tn0, sw1);
     if (A.qn0 != -1) {
+      const Row Qd = ld_tile(S.Qd, sw1);
       const double c = A.Rwv / A.Rgas - 1.0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Tv.x[j] = T.x[j] * fma(c, Tv.x[j] * fast_rcp(dp.x[j]), 1.0);
+      for (int j = 0; j < 4; ++j) Tv.x[j] *= fma(c, Qd.x[j] * fast_rcp(dp.x[j]), 1.0);
     }
     // vgp <- v.grad_p ; (gp0,gp1) <- -Rgas*T_v/p * grad_p  (the glnps terms of vtens, PO:219-228)
 #pragma unroll
@@ -381,47 +387,49 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
     Row& vt2 = gp1;
     Row& vgp = p;
 
-    // ---- grad T -> -v.grad T (PO:200-209)
+    // ---- w = Dinv.v: v.grad(s) = a_s*w1 + b_s*w2 with (a_s,b_s) the raw igp/jgp derivatives of s
+    // (PO/sphere_operators.cpp:21-47), and the divergence flux is metdet*dp*w (PO/sphere_operators.cpp:62-72):
+    // one pass over Dinv serves -v.grad T (PO:200-209) and divergence_sphere(v*dp) (PO:122)
+    Row w1, w2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 d01 = lds2(S.dinv + r * GS + j * 4), d23 = lds2(S.dinv + r * GS + j * 4 + 2);
+      w1.x[j] = fma(d01.x, v1.x[j], d01.y * v2.x[j]);
+      w2.x[j] = fma(d23.x, v1.x[j], d23.y * v2.x[j]);
+    }
     Row ttp;
     {
-      Row g0, g1;
-      gradient(T, S.dinv + r * GS, cx, A.dvv, g0, g1);
+      const Row T = ld_tile(S.Tn0, sw1);
+      const Row a = deriv_i(T, cx), b = deriv_j(T, A.dvv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ttp.x[j] = -fma(v1.x[j], g0.x[j], v2.x[j] * g1.x[j]);
+      for (int j = 0; j < 4; ++j) ttp.x[j] = -fma(a.x[j], w1.x[j], b.x[j] * w2.x[j]);
     }
 
     // ---- late inputs, first batch (vn0, dp3d(nm1), pecnd) must have landed
     mbar_wait(&S.bar[0], 0);
 
-    // ---- B2: vdp, derived_vn0 += eta_ave_w*vdp (PO:114-118), divergence_sphere(vdp) (PO/sphere_operators.cpp:50-89)
+    // ---- B2: derived_vn0 += eta_ave_w*v*dp (PO:114-118); divergence_sphere(v*dp) (PO/sphere_operators.cpp:50-89)
     Row divdp;
     {
-      Row u, ww2;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        u.x[j] = v1.x[j] * dp.x[j];
-        ww2.x[j] = v2.x[j] * dp.x[j];
-      }
       {
         Row a0, a1;
         ld_tile2(S.vn0, sw2, a0, a1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          a0.x[j] = fma(A.eta_ave_w, u.x[j], a0.x[j]);
-          a1.x[j] = fma(A.eta_ave_w, ww2.x[j], a1.x[j]);
+          a0.x[j] = fma(A.eta_ave_w, v1.x[j] * dp.x[j], a0.x[j]);
+          a1.x[j] = fma(A.eta_ave_w, v2.x[j] * dp.x[j], a1.x[j]);
         }
         st_tile2(S.vn0, sw2, a0, a1);
       }
       const Row met = ld_row(S.met + r * 4);
-      Row gv0, gv1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double2 d01 = lds2(S.dinv + r * GS + j * 4), d23 = lds2(S.dinv + r * GS + j * 4 + 2);
-        gv0.x[j] = met.x[j] * fma(d01.x, u.x[j], d01.y * ww2.x[j]);
-        gv1.x[j] = met.x[j] * fma(d23.x, u.x[j], d23.y * ww2.x[j]);
+        const double md = met.x[j] * dp.x[j];
+        w1.x[j] *= md;
+        w2.x[j] *= md;
       }
-      const Row dudx = deriv_i(gv0, cx);
-      const Row dvdy = deriv_j(gv1, A.dvv);
+      const Row dudx = deriv_i(w1, cx);
+      const Row dvdy = deriv_j(w2, A.dvv);
       const Row rm = ld_row(S.rmet + r * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) divdp.x[j] = (dudx.x[j] + dvdy.x[j]) * rm.x[j];  // dinv carries rrearth
@@ -443,7 +451,7 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
 #pragma unroll
       for (int j = 0; j < 4; ++j) kep.x[j] = fma(0.5, fma(v1.x[j], v1.x[j], v2.x[j] * v2.x[j]), pec.x[j]);
     }
-    // v1, v2, T are dead from here
+    // v1, v2 are dead from here
 
     // ---- D+E: the two vertical integrals in scan form
     //   q_k = Rgas*T_v*dp/p ; phi_k = phis + sum_{l>k} q_l + q_k/2              (PO:280-312)
@@ -573,7 +581,8 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   const encode_t encode = reinterpret_cast<encode_t>(fn);
   const cuuint64_t E = (cuuint64_t)a.nelem, L = (cuuint64_t)a.nlev, ntl = (cuuint64_t)a.ntl;
   struct Spec { CUtensorMap* m; const void* base; cuuint64_t rows; cuuint32_t box; const char* name; };
-  const Spec specs[7] = {
+  const Spec specs[8] = {
+      {&out->Qdp, a.Qdp, E * (cuuint64_t)a.qsize_d * 2 * L, (cuuint32_t)L, "Qdp"},
       {&out->dp3d, a.dp3d, E * ntl * L, (cuuint32_t)L, "dp3d"},
       {&out->T, a.T, E * ntl * L, (cuuint32_t)L, "T"},
       {&out->v, a.v, E * ntl * L * 2, (cuuint32_t)(2 * L), "v"},
