@@ -343,28 +343,8 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
       rp.x[j] = fast_rcp(p.x[j]);
     }
 
-    // ---- B1: grad_p; vgrad_p (PO:103-112); C: T_v (PO:126-156); glnps folded into the v tendencies
-    Row gp0, gp1;
-    gradient(p, S.dinv + r * GS, cx, A.dvv, gp0, gp1);
-    // from here on p is dead; only rp is kept
-    mbar_wait(&S.bar[2], 0);  // T(n0), Qdp tiles
-    Row Tv = ld_tile(S.Tn0, sw1);
-    if (A.qn0 != -1) {
-      const Row Qd = ld_tile(S.Qd, sw1);
-      const double c = A.Rwv / A.Rgas - 1.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Tv.x[j] *= fma(c, Qd.x[j] * fast_rcp(dp.x[j]), 1.0);
-    }
-    // vgp <- v.grad_p ; (gp0,gp1) <- -Rgas*T_v/p * grad_p  (the glnps terms of vtens, PO:219-228)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double vg = fma(v1.x[j], gp0.x[j], v2.x[j] * gp1.x[j]);
-      const double gl = -A.Rgas * (Tv.x[j] * rp.x[j]);
-      gp0.x[j] *= gl;
-      gp1.x[j] *= gl;
-      p.x[j] = vg;  // p now holds vgrad_p
-    }
-    // ---- vorticity_sphere (PO/sphere_operators.cpp:91-129) -> coriolis/vorticity terms of vtens
+    // ---- vorticity_sphere (PO/sphere_operators.cpp:91-129) first: it needs only v, and leaves one row (fv)
+    Row fv;
     {
       Row vc0, vc1;
 #pragma unroll
@@ -377,15 +357,35 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
       const Row dudy = deriv_j(vc0, A.dvv);
       const Row rm = ld_row(S.rmet + r * 4), fc = ld_row(S.fcor + r * 4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double fv = fma((dvdx.x[j] - dudy.x[j]) * rm.x[j], A.rrearth, fc.x[j]);
-        gp0.x[j] = fma(v2.x[j], fv, gp0.x[j]);   // vtens1 (without grad Ephi)
-        gp1.x[j] = fma(-v1.x[j], fv, gp1.x[j]);  // vtens2 (without grad Ephi)
-      }
+      for (int j = 0; j < 4; ++j) fv.x[j] = fma((dvdx.x[j] - dudy.x[j]) * rm.x[j], A.rrearth, fc.x[j]);
+    }
+    asm volatile("" ::: "memory");
+
+    // ---- B1: grad_p; vgrad_p (PO:103-112); C: T_v (PO:126-156); glnps folded into the v tendencies
+    Row gp0, gp1;
+    gradient(p, S.dinv + r * GS, cx, A.dvv, gp0, gp1);
+    // from here on p is dead; only rp is kept
+    mbar_wait(&S.bar[2], 0);  // T(n0), Qdp tiles
+    Row Tv = ld_tile(S.Tn0, sw1);
+    if (A.qn0 != -1) {
+      const Row Qd = ld_tile(S.Qd, sw1);
+      const double c = A.Rwv / A.Rgas - 1.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Tv.x[j] *= fma(c, Qd.x[j] * fast_rcp(dp.x[j]), 1.0);
+    }
+    // vgp <- v.grad_p ; vtens (without grad Ephi) = (+v2, -v1)*(fcor+vort) - Rgas*T_v/p * grad_p  (PO:219-228)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double vg = fma(v1.x[j], gp0.x[j], v2.x[j] * gp1.x[j]);
+      const double gl = -A.Rgas * (Tv.x[j] * rp.x[j]);
+      gp0.x[j] = fma(gl, gp0.x[j], v2.x[j] * fv.x[j]);
+      gp1.x[j] = fma(gl, gp1.x[j], -v1.x[j] * fv.x[j]);
+      p.x[j] = vg;  // p now holds vgrad_p
     }
     Row& vt1 = gp0;
     Row& vt2 = gp1;
     Row& vgp = p;
+    asm volatile("" ::: "memory");
 
     // ---- w = Dinv.v: v.grad(s) = a_s*w1 + b_s*w2 with (a_s,b_s) the raw igp/jgp derivatives of s
     // (PO/sphere_operators.cpp:21-47), and the divergence flux is metdet*dp*w (PO/sphere_operators.cpp:62-72):
