@@ -57,9 +57,7 @@ def ncu_traffic_per_launch(nelem, nlev):
     launch's element count (traffic is linear in elements); None until a capture exists."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        t = json.load(open(p))
-        if int(t["nlev"]) != nlev:
-            return None
+        t = json.load(open(p))["by_nlev"][str(nlev)]
         return float(t["dram_bytes_per_elem"]) * nelem
     except Exception:
         return None
@@ -188,6 +186,7 @@ def main():
     ap.add_argument("--nlev", type=int, default=72)
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="elements per pipeline chunk (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-target-s", type=float, default=15.0)
@@ -269,29 +268,26 @@ def main():
     # ---- end to end through the reference-facing host semantics: host arrays in, host arrays out, per step
     e2e = None
     if not args.no_e2e:
-        from tinman_sandbox_b200.capi import FIELD_NAMES, MUTATED_FIELDS
-        n0, np1, nm1, qn0 = [int(x) for x in td.ctl[2:6]]
-        ins = [n for n in FIELD_NAMES if n != "elem_derived_eta_dot_dpdn" or mode == tb.MODE_STRICT]
-        outs = [n for n in MUTATED_FIELDS if n != "elem_derived_eta_dot_dpdn" or mode == tb.MODE_STRICT]
-        h2d = sum(td.arrays[n].nbytes for n in ins)
-        d2h = sum(td.arrays[n].nbytes for n in outs)
-        h.upload(td.arrays, ins)
-        h.compute_and_apply_rhs(1, mode)
-        h.download(td.arrays, outs)
+        # every step: caar_run_host = copy-in of the slices the routine reads (pinned host arrays), the kernel,
+        # copy-out of the slices it writes, pipelined over element chunks; results are in the host arrays
+        h2d, d2h = h.host_traffic(mode)
+        h.compute_and_apply_rhs_host(td.arrays, mode, args.e2e_chunk)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            h.upload(td.arrays, ins)
-            h.compute_and_apply_rhs(1, mode)
-            h.download(td.arrays, outs)
+            h.compute_and_apply_rhs_host(td.arrays, mode, args.e2e_chunk)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * E * L * args.e2e_steps / float(t_e.item()), "unit": UNIT,
+        dt = float(t_e.item())
+        e2e = {"value": world * E * L * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-               "how": "caar_upload(all inputs, pinned host) + caar_run + caar_download(mutated arrays) per step"}
+               "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "pcie_gbs": {"h2d": h2d * args.e2e_steps / dt / 1e9, "d2h": d2h * args.e2e_steps / dt / 1e9},
+               "how": "caar_run_host per step: host arrays in, host arrays out (pinned), copy-in | kernel | "
+                      "copy-out pipelined over element chunks; PCIe-bound"}
     h.close()
 
     # ---- roofline of the dominant (only) kernel of a step

@@ -191,8 +191,29 @@ int caar_timer_stop(caar_handle h, float* ms);
    SQUARES so that ranks can all-reduce them before the sqrt. Synchronous. */
 int caar_norms(caar_handle h, int tl, int nets, int nete, double sumsq[3]);
 
-/* Reference-facing one-shot: upload(all) -> run(1) -> download(mutated) on `device`, i.e. exactly what
-   Homme::compute_and_apply_rhs(TestData&) means for host arrays. Creates and destroys a handle. */
+/* ---- the hot path on HOST arrays (what Homme::compute_and_apply_rhs(TestData&) means to its caller,
+   PO/compute_and_apply_rhs.hpp:9, called from the timed loop PO/main.cpp:113-121) ---- */
+/* ONE evaluation over [ctl->nets, ctl->nete) whose inputs are read from the caller's `host` arrays and whose
+   results are in the `host` arrays (and in the device mirrors) when the call returns. Only the slices the
+   routine actually reads travel host->device (time levels n0 and nm1 of dp3d/v/T, Qdp[qn0], vn0, pecnd,
+   omega_p, the 2-D geometry: 13 level-fields + 1664 B per element) and only what it writes travels back
+   (time level np1 of dp3d/v/T, vn0, phi, omega_p: 8 level-fields); every other host value is left
+   untouched, as in the reference. The element range is cut into chunks of `chunk_elems` elements
+   (0 = automatic) that flow through three CUDA streams — copy-in | kernel | copy-out — so that both PCIe
+   directions and the SMs work concurrently. Page-locked host arrays (caar_host_register, or
+   cudaMallocHost/torch pinned memory) are needed for the overlap; pageable memory works but serialises.
+   Synchronous. STRICT mode additionally moves eta_dot_dpdn both ways (the += 0 update of PO:164-171). */
+int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ctl, int mode, int chunk_elems);
+/* chunk_elems == CAAR_HOST_ZERO_COPY: no staging at all — the kernel reads the caller's arrays and writes the
+   results over PCIe itself (TMA / LDG / bulk stores on mapped host memory), one launch for the whole range.
+   Needs every array page-locked AND device-mapped (caar_host_register, cudaHostAlloc, torch pinned memory);
+   fails with CAAR_ERR_INVALID otherwise. The device mirrors are NOT updated on this path. */
+#define CAAR_HOST_ZERO_COPY (-1)
+/* bytes one caar_run_host call with this control moves in each direction */
+int caar_host_traffic(caar_handle h, const caar_control* ctl, int mode, size_t* h2d_bytes, size_t* d2h_bytes);
+
+/* Reference-facing one-shot: create -> set_params -> caar_run_host -> destroy on `device`, i.e. exactly what
+   Homme::compute_and_apply_rhs(TestData&) means for host arrays. */
 int caar_compute_and_apply_rhs_host(const caar_dims* dims, const caar_arrays* host,
                                     const caar_control* ctl, const caar_constants* c,
                                     const double dvv[16], double ps0, const double* hyai, int device,

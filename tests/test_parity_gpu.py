@@ -209,3 +209,67 @@ def test_errors_are_loud():
     with pytest.raises(tb.CaarError):
         h.compute_and_apply_rhs()
     h.close()
+
+
+def run_gpu_host(state, ncalls=1, mode=tb.MODE_FAST, chunk=0):
+    """The reference-facing call on HOST arrays (caar_run_host): no explicit upload/download."""
+    h = tb.Caar(state.nelem, state.nlev, state.qsize_d, state.ntl)
+    h.set_params(state.consts, state.dvv, state.ps0, state.hyai)
+    h.set_control(*[int(x) for x in state.ctl], dt2=state.dt2)
+    if chunk == tb.HOST_ZERO_COPY:
+        tb.host_register(state.arrays)
+    try:
+        for _ in range(ncalls):
+            h.compute_and_apply_rhs_host(state.arrays, mode, chunk)
+    finally:
+        if chunk == tb.HOST_ZERO_COPY:
+            tb.host_unregister(state.arrays)
+    traffic = h.host_traffic(mode)
+    h.close()
+    return traffic
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+@pytest.mark.parametrize("chunk", [0, 1, 7, 64, tb.HOST_ZERO_COPY])
+@pytest.mark.parametrize("qn0,tls", [(0, (0, 1, 2)), (-1, (2, 0, 1)), (1, (0, 1, 0)), (0, (1, 1, 1))])
+def test_streamed_host_call(mode, chunk, qn0, tls):
+    """caar_run_host: pipelined copy-in | kernel | copy-out over ragged element chunks moves only the slices
+    the routine reads/writes, and the host arrays end up exactly as the reference leaves them — every array,
+    including the values the routine does not touch (other time levels, the unused Qdp level, pecnd)."""
+    orc = oracle_for(72)
+    want = harness.randomize(harness.PortOracle().init(23), seed=77 + chunk)
+    want.ctl[0:2] = (2, 21)
+    want.ctl[2:5] = tls
+    want.ctl[5] = qn0
+    got = want.copy()
+    orc.run(want, 2, 2)
+    h2d, d2h = run_gpu_host(got, 2, mode, chunk)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+    # traffic accounting: 13 level-fields + geometry in, 8 out per element (fewer when levels alias / dry)
+    lf = 72 * 16 * 8
+    nlv = 1 if tls[0] == tls[2] else 2
+    extra = 73 * 16 * 8 if mode == tb.MODE_STRICT else 0
+    assert h2d == 19 * (1664 + (4 * nlv + (qn0 != -1) + 4) * lf + extra)
+    assert d2h == 19 * (8 * lf + extra)
+
+
+@pytest.mark.parametrize("chunk", [5, tb.HOST_ZERO_COPY])
+@pytest.mark.parametrize("nlev", [128, 24])
+def test_streamed_host_call_other_nlev(nlev, chunk):
+    """nlev=128 (TMA kernel) and nlev=24 (generic kernel) through both host paths; the staged path also takes
+    numpy (pageable) host memory."""
+    orc = oracle_for(nlev)
+    want = harness.randomize(harness.PortOracle().init(13, nlev), seed=3)
+    got = want.copy()
+    orc.run(want, 1, 2)
+    run_gpu_host(got, 1, tb.MODE_FAST, chunk)
+    check(got, want, exact=False)
+
+
+def test_zero_copy_needs_mapped_host_memory():
+    s = harness.PortOracle().init(3)
+    h = tb.Caar(3)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    with pytest.raises(tb.CaarError):
+        h.compute_and_apply_rhs_host(s.arrays, tb.MODE_FAST, tb.HOST_ZERO_COPY)
+    h.close()

@@ -14,10 +14,12 @@ the built extension.
 """
 from .capi import (  # noqa: F401
     Caar, CaarError, FIELD_NAMES, MUTATED_FIELDS, MODE_FAST, MODE_STRICT, lib_path, load_library,
-    field_shape, compute_and_apply_rhs, saxpby_host, EXPORTED_SYMBOLS,
+    field_shape, compute_and_apply_rhs, saxpby_host, EXPORTED_SYMBOLS, HOST_ZERO_COPY, host_register,
+    host_unregister,
 )
 
 __all__ = [
     "Caar", "CaarError", "FIELD_NAMES", "MUTATED_FIELDS", "MODE_FAST", "MODE_STRICT", "lib_path",
     "load_library", "field_shape", "compute_and_apply_rhs", "saxpby_host", "EXPORTED_SYMBOLS",
+    "HOST_ZERO_COPY", "host_register", "host_unregister",
 ]

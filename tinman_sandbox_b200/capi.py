@@ -31,7 +31,8 @@ MODE_FAST, MODE_STRICT = 0, 1
 EXPORTED_SYMBOLS = (
     "caar_last_error", "caar_version", "caar_field_count", "caar_device_count", "caar_create",
     "caar_destroy", "caar_set_params", "caar_set_stream", "caar_upload", "caar_download",
-    "caar_device_arrays", "caar_host_register", "caar_host_unregister", "caar_run", "caar_sync", "caar_launch_count", "caar_timer_start",
+    "caar_device_arrays", "caar_host_register", "caar_host_unregister", "caar_run", "caar_run_host",
+    "caar_host_traffic", "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
     "caar_saxpby_host",
 )
@@ -107,6 +108,9 @@ def load_library():
     lib.caar_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.caar_host_unregister.argtypes = [C.c_void_p]
     lib.caar_run.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.c_int]
+    lib.caar_run_host.argtypes = [C.c_void_p, C.POINTER(Arrays), C.POINTER(Control), C.c_int, C.c_int]
+    lib.caar_host_traffic.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_size_t)]
     lib.caar_sync.argtypes = [C.c_void_p]
     lib.caar_timer_start.argtypes = [C.c_void_p]
     lib.caar_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -218,6 +222,21 @@ class Caar:
         if sync:
             self.sync()
 
+    def compute_and_apply_rhs_host(self, arrays: dict, mode=MODE_FAST, chunk_elems=0):
+        """Homme::compute_and_apply_rhs(TestData&) on HOST arrays (PO/main.cpp:113-121 calls it this way):
+        inputs are read from `arrays`, results are in `arrays` on return; copy-in, kernel and copy-out are
+        pipelined over element chunks (caar_run_host)."""
+        st = _arrays_struct(arrays, FIELD_NAMES, self.shape_args)
+        _check(self.lib, self.lib.caar_run_host(self.h, C.byref(st), C.byref(self.control), mode, chunk_elems),
+               "caar_run_host")
+
+    def host_traffic(self, mode=MODE_FAST):
+        """(h2d_bytes, d2h_bytes) one compute_and_apply_rhs_host call moves with the current control."""
+        a, b = C.c_size_t(), C.c_size_t()
+        _check(self.lib, self.lib.caar_host_traffic(self.h, C.byref(self.control), mode, C.byref(a), C.byref(b)),
+               "caar_host_traffic")
+        return int(a.value), int(b.value)
+
     def sync(self):
         _check(self.lib, self.lib.caar_sync(self.h), "caar_sync")
 
@@ -260,6 +279,22 @@ def compute_and_apply_rhs(state, mode=MODE_FAST, device=0):
     rc = lib.caar_compute_and_apply_rhs_host(C.byref(dims), C.byref(st), C.byref(ctl), C.byref(c), _dp(dvv),
                                              float(state.ps0), _dp(hyai), device, mode)
     _check(lib, rc, "caar_compute_and_apply_rhs_host")
+
+
+HOST_ZERO_COPY = -1  # chunk_elems value selecting the zero-copy path of caar_run_host
+
+
+def host_register(arrays: dict):
+    """Page-locks and device-maps caller-owned numpy arrays in place (caar_host_register)."""
+    lib = load_library()
+    for n, a in arrays.items():
+        _check(lib, lib.caar_host_register(C.c_void_p(a.ctypes.data), a.nbytes), f"caar_host_register({n})")
+
+
+def host_unregister(arrays: dict):
+    lib = load_library()
+    for n, a in arrays.items():
+        _check(lib, lib.caar_host_unregister(C.c_void_p(a.ctypes.data)), f"caar_host_unregister({n})")
 
 
 def saxpby_host(a, b, x, y, sweeps=1, device=0):

@@ -2,10 +2,16 @@
 // compute entry point needs a CUDA device and fails with CAAR_ERR_CUDA otherwise.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 
 #include "caar_device.cuh"
+
+#ifndef CAAR_HOST_DEFAULT_ZERO_COPY
+#define CAAR_HOST_DEFAULT_ZERO_COPY 0  // chunk_elems == 0 uses the staged pipeline unless CAAR_HOST_PATH=zerocopy
+#endif
 
 namespace {
 
@@ -60,6 +66,14 @@ struct caar_handle_s {
   cudaEvent_t ev0, ev1;
   long long launches;
   caar::TmaMaps* tma;  // TMA descriptors of the device mirrors (nlev with a TMA-pipelined kernel only)
+  // caar_run_host pipeline: copy-in and copy-out streams, two events per element chunk (grown on demand)
+  cudaStream_t s_in, s_out;
+  cudaEvent_t* chunk_ev;
+  int n_chunk_ev;
+  cudaEvent_t ev_fence;
+  // caar_run_host zero-copy path: TMA descriptors over the caller's mapped host arrays, rebuilt when they move
+  caar::TmaMaps* tma_host;
+  double* tma_host_key[CAAR_NUM_FIELDS];
 };
 
 static_assert(sizeof(caar_arrays) == CAAR_NUM_FIELDS * sizeof(double*), "caar_arrays must be 16 pointers");
@@ -90,13 +104,14 @@ int validate_control(const caar_handle_s* h, const caar_control* ctl) {
   return CAAR_OK;
 }
 
-caar::KernelArgs make_args(const caar_handle_s* h, const caar_control* ctl) {
+caar::KernelArgs make_args(const caar_handle_s* h, const caar_control* ctl, double* const* ptr = nullptr) {
   caar::KernelArgs a;
   std::memset(&a, 0, sizeof a);
-  a.D = h->dev[0]; a.Dinv = h->dev[1]; a.fcor = h->dev[2]; a.spheremp = h->dev[3];
-  a.metdet = h->dev[4]; a.rmetdet = h->dev[5]; a.dp3d = h->dev[6]; a.v = h->dev[7];
-  a.T = h->dev[8]; a.phis = h->dev[9]; a.Qdp = h->dev[10]; a.eta_dot_dpdn = h->dev[11];
-  a.omega_p = h->dev[12]; a.phi = h->dev[13]; a.pecnd = h->dev[14]; a.vn0 = h->dev[15];
+  if (!ptr) ptr = h->dev;
+  a.D = ptr[0]; a.Dinv = ptr[1]; a.fcor = ptr[2]; a.spheremp = ptr[3];
+  a.metdet = ptr[4]; a.rmetdet = ptr[5]; a.dp3d = ptr[6]; a.v = ptr[7];
+  a.T = ptr[8]; a.phis = ptr[9]; a.Qdp = ptr[10]; a.eta_dot_dpdn = ptr[11];
+  a.omega_p = ptr[12]; a.phi = ptr[13]; a.pecnd = ptr[14]; a.vn0 = ptr[15];
   a.nelem = h->dims.nelem; a.nlev = h->dims.nlev; a.qsize_d = h->dims.qsize_d; a.ntl = h->dims.ntl;
   if (ctl) {
     a.nets = ctl->nets; a.nete = ctl->nete; a.n0 = ctl->n0; a.np1 = ctl->np1; a.nm1 = ctl->nm1;
@@ -153,6 +168,9 @@ int caar_create(caar_handle* out, const caar_dims* dims, int device) {
   cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fence, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
   for (int f = 0; f < CAAR_NUM_FIELDS && e == cudaSuccess; ++f) {
     const size_t bytes = field_count(*dims, f) * sizeof(double);
     e = cudaMalloc(&h->dev[f], bytes);
@@ -196,8 +214,14 @@ int caar_destroy(caar_handle h) {
   if (h->out3_host) cudaFreeHost(h->out3_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_fence) cudaEventDestroy(h->ev_fence);
+  for (int i = 0; i < h->n_chunk_ev; ++i) cudaEventDestroy(h->chunk_ev[i]);
+  delete[] h->chunk_ev;
+  if (h->s_in) cudaStreamSynchronize(h->s_in), cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamSynchronize(h->s_out), cudaStreamDestroy(h->s_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h->tma;
+  delete h->tma_host;
   delete h;
   return CAAR_OK;
 }
@@ -240,7 +264,7 @@ int caar_download(caar_handle h, const caar_arrays* host, unsigned mask) { retur
 
 int caar_host_register(void* ptr, size_t bytes) {
   if (!ptr || !bytes) return fail(CAAR_ERR_INVALID, "null argument");
-  CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   return CAAR_OK;
 }
 
@@ -272,6 +296,206 @@ int caar_run(caar_handle h, const caar_control* ctl, int nsteps, int mode) {
     CU_TRY(fast ? caar::launch_fused(a, h->stream) : caar::launch_strict(a, h->stream));
     ++h->launches;
   }
+  return CAAR_OK;
+}
+
+// ---- caar_run_host: one RHS evaluation on HOST arrays, pipelined over element chunks --------------------
+namespace {
+
+// one contiguous run of doubles inside every element's block of a field
+struct Slice {
+  int f;            // field index (order of caar_arrays)
+  size_t per_elem;  // doubles per element of the whole field
+  size_t off, len;  // the run [off, off+len) inside the element's block
+};
+
+// true when every host array is page-locked and mapped into the device address space; dev[] = device aliases
+bool host_arrays_mapped(double* const* tab, double** dev) {
+  for (int f = 0; f < CAAR_NUM_FIELDS; ++f) {
+    dev[f] = nullptr;
+    if (!tab[f]) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, tab[f]) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    dev[f] = static_cast<double*>(at.devicePointer);
+  }
+  return true;
+}
+
+bool zero_copy_default() {
+  static const int v = [] {
+    const char* e = getenv("CAAR_HOST_PATH");  // "staged" | "zerocopy"
+    if (e && std::strcmp(e, "staged") == 0) return 0;
+    if (e && std::strcmp(e, "zerocopy") == 0) return 1;
+    return CAAR_HOST_DEFAULT_ZERO_COPY;
+  }();
+  return v != 0;
+}
+
+int add_levels(Slice* out, int n, int f, size_t lf, int ntl, int tl_a, int tl_b) {
+  out[n++] = Slice{f, lf * ntl, lf * tl_a, lf};
+  if (tl_b != tl_a) out[n++] = Slice{f, lf * ntl, lf * tl_b, lf};
+  return n;
+}
+
+cudaError_t copy_slice(const Slice& s, double* dev, double* host, int e0, int e1, bool to_device, cudaStream_t st) {
+  const size_t n = (size_t)(e1 - e0);
+  double* d = dev + (size_t)e0 * s.per_elem + s.off;
+  double* h = host + (size_t)e0 * s.per_elem + s.off;
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  if (s.len == s.per_elem)
+    return to_device ? cudaMemcpyAsync(d, h, n * s.len * sizeof(double), kind, st)
+                     : cudaMemcpyAsync(h, d, n * s.len * sizeof(double), kind, st);
+  const size_t pitch = s.per_elem * sizeof(double), width = s.len * sizeof(double);
+  // Pitched DMA over PCIe runs markedly slower with 18 KB rows than with 9 KB rows while the other direction
+  // is busy (measured: tools/pcie_probe.cu, profiles/README.md), so wide rows are cut into pieces of <= row_max B
+  static const size_t row_max = [] { const char* e = getenv("CAAR_HOST_ROW"); return e ? (size_t)atol(e) : (size_t)9216; }();
+  static const int split_dirs = [] { const char* e = getenv("CAAR_HOST_SPLIT"); return e ? atoi(e) : 3; }();  // 1 = in, 2 = out
+  if (row_max > 0 && width > row_max && (split_dirs & (to_device ? 1 : 2))) {
+    for (size_t o = 0; o < width; o += row_max) {
+      const size_t wd = (width - o < row_max) ? width - o : row_max;
+      const cudaError_t e = to_device ? cudaMemcpy2DAsync((char*)d + o, pitch, (char*)h + o, pitch, wd, n, kind, st)
+                                      : cudaMemcpy2DAsync((char*)h + o, pitch, (char*)d + o, pitch, wd, n, kind, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  return to_device ? cudaMemcpy2DAsync(d, pitch, h, pitch, width, n, kind, st)
+                   : cudaMemcpy2DAsync(h, pitch, d, pitch, width, n, kind, st);
+}
+
+}  // namespace
+
+int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ctl, int mode, int chunk_elems) {
+  if (!h || !host) return fail(CAAR_ERR_INVALID, "null argument");
+  if (!h->params_set) return fail(CAAR_ERR_STATE, "caar_set_params must be called before caar_run_host");
+  if (int rc = validate_control(h, ctl)) return rc;
+  if (mode != CAAR_MODE_FAST && mode != CAAR_MODE_STRICT) return fail(CAAR_ERR_INVALID, "mode=%d", mode);
+  if (chunk_elems < 0 && chunk_elems != CAAR_HOST_ZERO_COPY) return fail(CAAR_ERR_INVALID, "chunk_elems=%d", chunk_elems);
+  const caar_dims& d = h->dims;
+  const bool fast = (mode == CAAR_MODE_FAST) && caar::fused_supports(d.nlev);
+  if (!fast && caar::strict_smem_bytes(d.nlev) > 200 * 1024)
+    return fail(CAAR_ERR_UNSUPPORTED, "nlev=%d too large for the strict kernel", d.nlev);
+  const int n = ctl->nete - ctl->nets;
+  if (n == 0) return CAAR_OK;
+
+  // the slices the routine reads (PO/compute_and_apply_rhs.cpp:74-257) and writes (:117,161,172-173,251-254)
+  const size_t lf = (size_t)d.nlev * 16;
+  Slice in[24], out[8];
+  int ni = 0, no = 0;
+  for (int f : {0, 1, 2, 3, 4, 5, 9}) in[ni++] = Slice{f, field_count(d, f) / d.nelem, 0, field_count(d, f) / d.nelem};
+  ni = add_levels(in, ni, 6, lf, d.ntl, ctl->n0, ctl->nm1);
+  ni = add_levels(in, ni, 7, 2 * lf, d.ntl, ctl->n0, ctl->nm1);
+  ni = add_levels(in, ni, 8, lf, d.ntl, ctl->n0, ctl->nm1);
+  if (ctl->qn0 != -1) in[ni++] = Slice{10, lf * 2 * d.qsize_d, lf * ctl->qn0, lf};
+  in[ni++] = Slice{12, lf, 0, lf};
+  in[ni++] = Slice{14, lf, 0, lf};
+  in[ni++] = Slice{15, 2 * lf, 0, 2 * lf};
+  out[no++] = Slice{6, lf * d.ntl, lf * ctl->np1, lf};
+  out[no++] = Slice{7, 2 * lf * d.ntl, 2 * lf * ctl->np1, 2 * lf};
+  out[no++] = Slice{8, lf * d.ntl, lf * ctl->np1, lf};
+  out[no++] = Slice{12, lf, 0, lf};
+  out[no++] = Slice{13, lf, 0, lf};
+  out[no++] = Slice{15, 2 * lf, 0, 2 * lf};
+  if (!fast) {  // the reference-order kernel also performs eta_dot_dpdn += eta_ave_w*0 (PO:164-171)
+    const size_t le = (size_t)(d.nlev + 1) * 16;
+    in[ni++] = Slice{11, le, 0, le};
+    out[no++] = Slice{11, le, 0, le};
+  }
+  double* const* tab = as_table(host);
+  for (int i = 0; i < ni; ++i)
+    if (!tab[in[i].f]) return fail(CAAR_ERR_INVALID, "host pointer of field %d is null", in[i].f);
+  for (int i = 0; i < no; ++i)
+    if (!tab[out[i].f]) return fail(CAAR_ERR_INVALID, "host pointer of field %d is null", out[i].f);
+
+  DeviceGuard guard(h->device);
+  // ---- zero-copy path: the kernel itself reads the caller's arrays over PCIe (TMA / LDG on mapped host memory)
+  // and writes the results straight back: one launch, both link directions busy, no staging copies
+  double* mapped[CAAR_NUM_FIELDS];
+  const bool can_map = host_arrays_mapped(tab, mapped);
+  if (chunk_elems == CAAR_HOST_ZERO_COPY && !can_map)
+    return fail(CAAR_ERR_INVALID, "CAAR_HOST_ZERO_COPY needs page-locked, device-mapped host arrays "
+                                  "(caar_host_register / cudaHostAlloc)");
+  if (can_map && (chunk_elems == CAAR_HOST_ZERO_COPY || (chunk_elems == 0 && zero_copy_default()))) {
+    caar::KernelArgs za = make_args(h, ctl, mapped);
+    za.tma = nullptr;
+    za.pf_dist = -1;  // no L2 prefetch of host memory
+    if (d.nlev == 72 || d.nlev == 128) {
+      if (!h->tma_host || std::memcmp(h->tma_host_key, mapped, sizeof mapped) != 0) {
+        if (!h->tma_host) h->tma_host = new (std::nothrow) caar::TmaMaps();
+        char msg[256] = "host allocation failed";
+        if (!h->tma_host || caar::build_tma_maps(h->tma_host, za, msg, sizeof msg)) {
+          delete h->tma_host;
+          h->tma_host = nullptr;
+          return fail(CAAR_ERR_CUDA, "caar_run_host: %s", msg);
+        }
+        std::memcpy(h->tma_host_key, mapped, sizeof mapped);
+      }
+      za.tma = h->tma_host;
+    }
+    CU_TRY(fast ? caar::launch_fused(za, h->stream) : caar::launch_strict(za, h->stream));
+    ++h->launches;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return CAAR_OK;
+  }
+
+  // ---- staged path. Chunking: enough chunks to hide the first copy-in and the last copy-out, big enough to keep
+  // every SM busy
+  int chunk = chunk_elems;
+  if (chunk == 0) {
+    chunk = (n + 47) / 48;
+    if (chunk < 296) chunk = 296;
+    if (chunk > 4096) chunk = 4096;
+  }
+  const int nchunks = (n + chunk - 1) / chunk;
+  if (h->n_chunk_ev < 2 * nchunks) {
+    cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[2 * nchunks];
+    if (!ev) return fail(CAAR_ERR_NOMEM, "host allocation failed");
+    for (int i = 0; i < h->n_chunk_ev; ++i) ev[i] = h->chunk_ev[i];
+    delete[] h->chunk_ev;
+    h->chunk_ev = ev;
+    while (h->n_chunk_ev < 2 * nchunks) {
+      CU_TRY(cudaEventCreateWithFlags(&h->chunk_ev[h->n_chunk_ev], cudaEventDisableTiming));
+      ++h->n_chunk_ev;
+    }
+  }
+  // the copy-in stream must not overtake work already queued on the compute stream (it rewrites the mirrors)
+  CU_TRY(cudaEventRecord(h->ev_fence, h->stream));
+  CU_TRY(cudaStreamWaitEvent(h->s_in, h->ev_fence, 0));
+  caar::KernelArgs a = make_args(h, ctl);
+  for (int c = 0; c < nchunks; ++c) {
+    const int e0 = ctl->nets + c * chunk, e1 = (e0 + chunk < ctl->nete) ? e0 + chunk : ctl->nete;
+    for (int i = 0; i < ni; ++i) CU_TRY(copy_slice(in[i], h->dev[in[i].f], tab[in[i].f], e0, e1, true, h->s_in));
+    CU_TRY(cudaEventRecord(h->chunk_ev[2 * c], h->s_in));
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->chunk_ev[2 * c], 0));
+    a.nets = e0;
+    a.nete = e1;
+    CU_TRY(fast ? caar::launch_fused(a, h->stream) : caar::launch_strict(a, h->stream));
+    ++h->launches;
+    CU_TRY(cudaEventRecord(h->chunk_ev[2 * c + 1], h->stream));
+    CU_TRY(cudaStreamWaitEvent(h->s_out, h->chunk_ev[2 * c + 1], 0));
+    for (int i = 0; i < no; ++i) CU_TRY(copy_slice(out[i], h->dev[out[i].f], tab[out[i].f], e0, e1, false, h->s_out));
+  }
+  CU_TRY(cudaStreamSynchronize(h->s_out));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return CAAR_OK;
+}
+
+int caar_host_traffic(caar_handle h, const caar_control* ctl, int mode, size_t* h2d_bytes, size_t* d2h_bytes) {
+  if (!h || !ctl || !h2d_bytes || !d2h_bytes) return fail(CAAR_ERR_INVALID, "null argument");
+  if (int rc = validate_control(h, ctl)) return rc;
+  const caar_dims& d = h->dims;
+  const bool fast = (mode == CAAR_MODE_FAST) && caar::fused_supports(d.nlev);
+  const size_t lf = (size_t)d.nlev * 16, le = (size_t)(d.nlev + 1) * 16;
+  const size_t lv = (ctl->n0 == ctl->nm1) ? 1 : 2;
+  size_t in = 2 * 64 + 5 * 16 + lv * 4 * lf + (ctl->qn0 != -1 ? lf : 0) + 4 * lf + (fast ? 0 : le);
+  size_t out = 8 * lf + (fast ? 0 : le);
+  const size_t n = (size_t)(ctl->nete - ctl->nets);
+  *h2d_bytes = in * n * sizeof(double);
+  *d2h_bytes = out * n * sizeof(double);
   return CAAR_OK;
 }
 
@@ -321,9 +545,7 @@ int caar_compute_and_apply_rhs_host(const caar_dims* dims, const caar_arrays* ho
   int rc = caar_create(&h, dims, device);
   if (rc) return rc;
   rc = caar_set_params(h, c, dvv, ps0, hyai);
-  if (!rc) rc = caar_upload(h, host, CAAR_F_ALL);
-  if (!rc) rc = caar_run(h, ctl, 1, mode);
-  if (!rc) rc = caar_download(h, host, CAAR_F_MUTATED);
+  if (!rc) rc = caar_run_host(h, host, ctl, mode, 0);
   char keep[sizeof g_err];
   std::memcpy(keep, g_err, sizeof keep);
   caar_destroy(h);

@@ -621,7 +621,7 @@ cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
     return v ? atoi(v) : -1;
   }();
   // default distance 148 elements (one CTA per SM ahead): best of a 0/74/148/296/592 sweep at ne=120
-  a.pf_dist = pf_env >= 0 ? pf_env : 148;
+  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : 148);
   switch (a.nlev) {
     case 72: return launch_L<72>(a, s);
     case 128: return launch_L<128>(a, s);

@@ -286,11 +286,7 @@ int main(int argc, char** argv) {
           OK(caar_run(r.h, &ctl, o.num_exec, o.mode));
           OK(caar_sync(r.h));
         } else {
-          for (int it = 0; it < o.num_exec; ++it) {
-            OK(caar_upload(r.h, &r.host, CAAR_F_ALL));
-            OK(caar_run(r.h, &ctl, 1, o.mode));
-            OK(caar_download(r.h, &r.host, CAAR_F_MUTATED));
-          }
+          for (int it = 0; it < o.num_exec; ++it) OK(caar_run_host(r.h, &r.host, &ctl, o.mode, 0));
         }
       });
     for (auto& t : pool) t.join();

@@ -11,9 +11,10 @@
 //   Homme::print_results_2norm                PO/compute_and_apply_rhs.cpp:372  (same text format)
 //   Homme::dump_results_to_file               PO/compute_and_apply_rhs.cpp:401  (same four files)
 //
-// Semantics: the host arrays are the truth, exactly as in the reference. Each call uploads the inputs,
-// runs one RHS evaluation on the GPU and downloads the arrays the routine mutates, so the driver's later
-// reads (norms, dumps) see the results. A handle is created on first use and kept for the process
+// Semantics: the host arrays are the truth, exactly as in the reference. Each call streams the slices the
+// routine reads to the GPU, runs one RHS evaluation and streams back the slices it writes (caar_run_host:
+// copy-in | kernel | copy-out pipelined over element chunks), so the driver's later reads (norms, dumps) see
+// the results. A handle is created on first use and kept for the process
 // (device mirrors are reused between calls); the caller's arrays are page-locked in place on first use
 // (CAAR_PIN=0 disables) so the copies run at PCIe speed. Errors abort with a message, like the reference's
 // own failure paths (std::abort, PO/compute_and_apply_rhs.cpp:414-445).
@@ -127,9 +128,7 @@ void compute_and_apply_rhs(TestData& data) {
   caar_control ctl = {data.control.nets, data.control.nete, data.control.n0, data.control.np1,
                       data.control.nm1, data.control.qn0, data.control.dt2};
   const caar_arrays host = view(data.arrays);
-  if (int rc = caar_upload(s.h, &host, CAAR_F_ALL)) die("caar_upload", rc);
-  if (int rc = caar_run(s.h, &ctl, 1, s.mode)) die("caar_run", rc);
-  if (int rc = caar_download(s.h, &host, CAAR_F_MUTATED)) die("caar_download", rc);
+  if (int rc = caar_run_host(s.h, &host, &ctl, s.mode, 0)) die("caar_run_host", rc);
 }
 
 // sqrt of a compensated (Kahan) sum of squares — what the driver's norm check is built on
