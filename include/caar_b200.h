@@ -165,6 +165,29 @@ int caar_set_stream(caar_handle h, void* cuda_stream);
 int caar_upload(caar_handle h, const caar_arrays* host, unsigned field_mask);
 int caar_download(caar_handle h, const caar_arrays* host, unsigned field_mask);
 
+/* ---- second host layout: Fortran flat pointers (SURVEY §8b "alt boundary") ----
+   CAAR_LAYOUT_CXX is the layout above. CAAR_LAYOUT_F90 is the memory order of the Fortran arrays themselves
+   (F/element_state_mod.F90:17-23, F/element_mod.F90:69-121), element index slowest, exactly what HOMMEXX's
+   Elements::init_2d / pull_from_f90_pointers / push_to_f90_pointers read and write
+   (LV/Elements.hpp:92-117, LV/Elements.cpp:48-99,154-435):
+     fcor, spheremp, metdet, rmetdet, phis  (np,np,nelemd)            = [ie][j][i]
+     D, Dinv                                (np,np,2,2,nelemd)        = [ie][b][a][j][i]
+     dp3d, T                                (np,np,nlev,tl,nelemd)    = [ie][tl][lev][j][i]
+     v                                      (np,np,2,nlev,tl,nelemd)  = [ie][tl][lev][c][j][i]
+     Qdp                                    (np,np,nlev,qsize_d,2,nelemd) = [ie][qni][iq][lev][j][i]
+     eta_dot_dpdn (nlev+1), omega_p, phi, pecnd (np,np,nlev,nelemd)   = [ie][lev][j][i]
+     vn0                                    (np,np,2,nlev,nelemd)     = [ie][lev][c][j][i]
+   (the reference's C++ [igp][jgp] equals Fortran (i,j) index for index, so every 4x4 block is transposed in
+   memory). The device layout does not change: the copies pass through a device staging buffer and a relayout
+   kernel, the hot kernels are the same. With CAAR_LAYOUT_F90 a NULL elem_rmetdet is accepted on upload
+   (HOMMEXX passes none): rmetdet = 1/metdet is then computed on the device. */
+enum { CAAR_LAYOUT_CXX = 0, CAAR_LAYOUT_F90 = 1 };
+int caar_upload_layout(caar_handle h, const caar_arrays* host, unsigned field_mask, int layout);
+int caar_download_layout(caar_handle h, const caar_arrays* host, unsigned field_mask, int layout);
+/* caar_set_params with Dvv in Fortran memory order (deriv%Dvv(np,np), LV/Derivative.cpp:11-23) */
+int caar_set_params_f90(caar_handle h, const caar_constants* c, const double dvv_f90[16], double ps0,
+                        const double* hyai);
+
 /* Page-lock / unlock a caller-owned host range in place (cudaHostRegister), so that later
    caar_upload/caar_download of it are DMA copies at PCIe speed. Optional. */
 int caar_host_register(void* ptr, size_t bytes);
@@ -178,6 +201,13 @@ int caar_device_arrays(caar_handle h, caar_arrays* dev_out);
    handle's stream. Identical to calling the reference routine nsteps times with the same Control
    (PO/main.cpp:113-121: no time-level rotation between calls). mode = CAAR_MODE_*. */
 int caar_run(caar_handle h, const caar_control* ctl, int nsteps, int mode);
+/* Time stepping on the resident state: nsteps evaluations with the reference's leapfrog
+   rotation of the time levels after each one — TestData::update_time_levels, PO/data_structures.cpp:174-180
+   (np1 <- nm1, nm1 <- n0, n0 <- old np1), the call the reference driver keeps next to its timed loop
+   (PO/main.cpp:118). Asynchronous like caar_run; *ctl holds the rotated levels on return. Aliased levels
+   (nm1 = np1 = n0: forward Euler / RK stages, F/routine_extracted.F90:6-16) are legal in every entry point. */
+int caar_run_stepping(caar_handle h, caar_control* ctl, int nsteps, int mode);
+void caar_update_time_levels(caar_control* ctl);
 int caar_sync(caar_handle h);
 /* number of kernel launches issued by caar_run/caar_norms on this handle since creation */
 long long caar_launch_count(caar_handle h);

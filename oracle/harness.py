@@ -252,3 +252,34 @@ def randomize(s: State, seed=20261018):
     s.ps0 = 1.0e3
     s.hyai[...] = np.linspace(0.002, 0.0, L + 1)
     return s
+
+
+# ---- Fortran (F90 flat pointer) memory order of every array — test-side restatement of the convention HOMMEXX
+# reads its F90 pointers in (level_vectorized_ppscan/Elements.cpp:48-99,164-292; the Fortran declarations are
+# fortran/element_state_mod.F90:17-23 and fortran/element_mod.F90:69-121). C++ [igp][jgp] == Fortran (i,j).
+_F90_AXES = {
+    "elem_D": (0, 4, 3, 2, 1), "elem_Dinv": (0, 4, 3, 2, 1),                       # [e][b][a][j][i]
+    "elem_fcor": (0, 2, 1), "elem_spheremp": (0, 2, 1), "elem_metdet": (0, 2, 1),  # [e][j][i]
+    "elem_rmetdet": (0, 2, 1), "elem_state_phis": (0, 2, 1),
+    "elem_state_dp3d": (0, 1, 2, 4, 3), "elem_state_T": (0, 1, 2, 4, 3),           # [e][tl][lev][j][i]
+    "elem_state_v": (0, 1, 2, 5, 4, 3),                                            # [e][tl][lev][c][j][i]
+    "elem_state_Qdp": (0, 2, 1, 3, 5, 4),                                          # [e][qni][iq][lev][j][i]
+    "elem_derived_eta_dot_dpdn": (0, 1, 3, 2), "elem_derived_omega_p": (0, 1, 3, 2),
+    "elem_derived_phi": (0, 1, 3, 2), "elem_derived_pecnd": (0, 1, 3, 2),          # [e][lev][j][i]
+    "elem_derived_vn0": (0, 1, 4, 3, 2),                                           # [e][lev][c][j][i]
+}
+
+
+def to_f90(arrays: dict) -> dict:
+    """C++ (pointers_only) layout -> Fortran memory order, as new contiguous arrays."""
+    return {n: np.ascontiguousarray(a.transpose(_F90_AXES[n])) for n, a in arrays.items()}
+
+
+def from_f90(f90: dict) -> dict:
+    """Fortran memory order -> C++ (pointers_only) layout."""
+    out = {}
+    for n, a in f90.items():
+        ax = _F90_AXES[n]
+        inv = np.argsort(ax)
+        out[n] = np.ascontiguousarray(a.transpose(inv))
+    return out

@@ -137,3 +137,22 @@ def test_saxpby_port():
         w2 = 3.0 * x2 + 5.0 * y2
         harness.RefSaxpby().run(3.0, 5.0, x2, y2, 1)
         assert np.array_equal(x2, w2)
+
+
+def test_f90_layout_convention_against_fortran_golden(port, golden_dir):
+    """The Fortran memory order used for the F90 boundary (harness.to_f90) is the one the reference's Fortran
+    KAT is written in: T(:,:,:,np1) and v(:,:,1:2,:,np1) of element 1, flattened, ARE Ttest / v1test / v2test
+    (fortran/test_mod.F90), with no transposition left to do."""
+    g = np.load(os.path.join(golden_dir, "fortran_golden.npz"))
+    s = port.init(3)
+    s.dvv[...] = s.dvv.astype(np.float32).astype(np.float64)
+    port.run(s)
+    f = harness.to_f90({n: s.arrays[n] for n in ("elem_state_T", "elem_state_v")})
+    assert np.array_equal(f["elem_state_T"][0, 1].reshape(-1), g["Ttest"])
+    v = f["elem_state_v"][0, 1]                      # [lev][c][j][i]
+    for c, key in ((0, "v1test"), (1, "v2test")):
+        got = v[:, c].reshape(-1)
+        assert np.max(np.abs(got - g[key])) / np.max(np.abs(g[key])) < 1e-14
+    back = harness.from_f90(harness.to_f90(s.arrays))
+    for n in harness.FIELD_NAMES:
+        assert np.array_equal(back[n], s.arrays[n]), n

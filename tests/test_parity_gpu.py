@@ -273,3 +273,72 @@ def test_zero_copy_needs_mapped_host_memory():
     with pytest.raises(tb.CaarError):
         h.compute_and_apply_rhs_host(s.arrays, tb.MODE_FAST, tb.HOST_ZERO_COPY)
     h.close()
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+@pytest.mark.parametrize("nlev,qsize_d", [(72, 1), (72, 3), (24, 2)])
+def test_f90_flat_pointer_boundary(mode, nlev, qsize_d):
+    """SURVEY §8f rank 1 / §8b alt boundary: arrays in Fortran memory order in, Fortran memory order out
+    (caar_upload_layout / caar_download_layout with CAAR_LAYOUT_F90, Dvv through caar_set_params_f90, no
+    rmetdet passed — HOMMEXX has none). Same results as the reference on the same values."""
+    orc = harness.PortOracle() if (nlev != 72 or qsize_d != 1) else oracle_for(72)
+    want = harness.randomize(harness.PortOracle().init(11, nlev, qsize_d), seed=21 + qsize_d)
+    want.arrays["elem_rmetdet"][...] = 1.0 / want.arrays["elem_metdet"]
+    f90 = harness.to_f90(want.arrays)
+    del f90["elem_rmetdet"]
+    orc.run(want, 2, 2)
+    h = tb.Caar(want.nelem, nlev, qsize_d, want.ntl)
+    h.set_params_f90(want.consts, np.ascontiguousarray(want.dvv.T), want.ps0, want.hyai)
+    h.set_control(*[int(x) for x in want.ctl], dt2=want.dt2)
+    h.upload_f90(f90)
+    h.compute_and_apply_rhs(2, mode)
+    f90["elem_rmetdet"] = np.zeros_like(f90["elem_metdet"])
+    h.download_f90(f90, names=None)
+    h.close()
+    got = want.copy()
+    got.arrays = harness.from_f90(f90)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+
+
+def test_f90_boundary_against_fortran_golden(golden_dir):
+    """The Fortran KAT (fortran/test_mod.F90) read straight out of the F90-layout download: no transposes."""
+    g = np.load(os.path.join(golden_dir, "fortran_golden.npz"))
+    s = harness.PortOracle().init(3)
+    f90 = harness.to_f90(s.arrays)
+    h = tb.Caar(3)
+    dvv32 = s.dvv.astype(np.float32).astype(np.float64)
+    h.set_params_f90(s.consts, np.ascontiguousarray(dvv32.T), s.ps0, s.hyai)
+    h.upload_f90(f90)
+    h.compute_and_apply_rhs(1, tb.MODE_STRICT)
+    h.download_f90(f90)
+    h.close()
+    assert np.array_equal(f90["elem_state_T"][0, 1].reshape(-1), g["Ttest"])
+    assert rel_err(f90["elem_state_v"][0, 1][:, 0].reshape(-1), g["v1test"]) < 1e-14
+    assert rel_err(f90["elem_state_v"][0, 1][:, 1].reshape(-1), g["v2test"]) < 1e-14
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+def test_leapfrog_stepping_with_time_level_rotation(mode):
+    """SURVEY §8f rank 2: caar_run_stepping = call + TestData::update_time_levels, 5 steps, against the
+    reference doing the same on the CPU (PO/main.cpp:116-118 with the rotation enabled)."""
+    orc = oracle_for(72)
+    want = harness.randomize(harness.PortOracle().init(7), seed=12)
+    want.dt2 = 0.5
+    got = want.copy()
+    for _ in range(5):
+        orc.run(want, 1, 1)
+        nets, nete, n0, np1, nm1, qn0 = [int(x) for x in want.ctl]
+        want.ctl[:] = (nets, nete, np1, nm1, n0, qn0)
+    h = tb.Caar(got.nelem, got.nlev)
+    h.set_params(got.consts, got.dvv, got.ps0, got.hyai)
+    h.set_control(*[int(x) for x in got.ctl], dt2=got.dt2)
+    h.upload(got.arrays)
+    h.run_stepping(5, mode)
+    h.download(got.arrays, names=None)
+    assert (h.control.n0, h.control.np1, h.control.nm1) == tuple(int(x) for x in want.ctl[2:5])
+    h.close()
+    for n in harness.FIELD_NAMES:
+        if mode == tb.MODE_STRICT or n not in harness.MUTATED:
+            assert np.array_equal(got.arrays[n], want.arrays[n]), n
+        else:  # rounding differences are amplified by the 5 dependent steps: 1e-12 per step
+            assert rel_err(got.arrays[n], want.arrays[n]) <= 5 * TOL, n

@@ -26,13 +26,15 @@ MUTATED_FIELDS = ("elem_state_dp3d", "elem_state_v", "elem_state_T", "elem_deriv
 F_ALL = 0xFFFF
 F_MUTATED = sum(FIELD_BIT[n] for n in MUTATED_FIELDS)
 MODE_FAST, MODE_STRICT = 0, 1
+LAYOUT_CXX, LAYOUT_F90 = 0, 1
 
 # every symbol include/caar_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "caar_last_error", "caar_version", "caar_field_count", "caar_device_count", "caar_create",
     "caar_destroy", "caar_set_params", "caar_set_stream", "caar_upload", "caar_download",
     "caar_device_arrays", "caar_host_register", "caar_host_unregister", "caar_run", "caar_run_host",
-    "caar_host_traffic", "caar_sync", "caar_launch_count", "caar_timer_start",
+    "caar_host_traffic", "caar_upload_layout", "caar_download_layout", "caar_set_params_f90", "caar_run_stepping",
+    "caar_update_time_levels", "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
     "caar_saxpby_host",
 )
@@ -111,6 +113,13 @@ def load_library():
     lib.caar_run_host.argtypes = [C.c_void_p, C.POINTER(Arrays), C.POINTER(Control), C.c_int, C.c_int]
     lib.caar_host_traffic.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.POINTER(C.c_size_t),
                                       C.POINTER(C.c_size_t)]
+    lib.caar_run_stepping.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.c_int]
+    lib.caar_update_time_levels.argtypes = [C.POINTER(Control)]
+    lib.caar_update_time_levels.restype = None
+    lib.caar_upload_layout.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int]
+    lib.caar_download_layout.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int]
+    lib.caar_set_params_f90.argtypes = [C.c_void_p, C.POINTER(Constants), C.POINTER(C.c_double), C.c_double,
+                                        C.POINTER(C.c_double)]
     lib.caar_sync.argtypes = [C.c_void_p]
     lib.caar_timer_start.argtypes = [C.c_void_p]
     lib.caar_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -206,6 +215,37 @@ class Caar:
         st = _arrays_struct(arrays, names, self.shape_args)
         _check(self.lib, self.lib.caar_upload(self.h, C.byref(st), _mask(names)), "caar_upload")
 
+    def upload_f90(self, arrays: dict, names=None):
+        """Upload arrays held in Fortran memory order (CAAR_LAYOUT_F90, see include/caar_b200.h); only the flat
+        sizes are checked. `elem_rmetdet` may be absent: it is then computed on the device as 1/metdet."""
+        names = FIELD_NAMES if names is None else names
+        st = Arrays()
+        for n in names:
+            if n == "elem_rmetdet" and n not in arrays:
+                continue
+            a = arrays[n]
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.size != int(np.prod(field_shape(n, *self.shape_args))):
+                raise CaarError(f"{n}: need a contiguous float64 array of the field's size")
+            setattr(st, n, _dp(a))
+        _check(self.lib, self.lib.caar_upload_layout(self.h, C.byref(st), _mask(names), LAYOUT_F90), "caar_upload_layout")
+
+    def download_f90(self, arrays: dict, names=MUTATED_FIELDS):
+        names = FIELD_NAMES if names is None else names
+        st = Arrays()
+        for n in names:
+            a = arrays[n]
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.size != int(np.prod(field_shape(n, *self.shape_args))):
+                raise CaarError(f"{n}: need a contiguous float64 array of the field's size")
+            setattr(st, n, _dp(a))
+        _check(self.lib, self.lib.caar_download_layout(self.h, C.byref(st), _mask(names), LAYOUT_F90), "caar_download_layout")
+
+    def set_params_f90(self, consts, dvv_f90, ps0, hyai):
+        c = Constants(*[float(x) for x in consts])
+        dvv = np.ascontiguousarray(dvv_f90, dtype=np.float64).reshape(16)
+        hyai = np.ascontiguousarray(hyai, dtype=np.float64)
+        _check(self.lib, self.lib.caar_set_params_f90(self.h, C.byref(c), _dp(dvv), float(ps0), _dp(hyai)),
+               "caar_set_params_f90")
+
     def download(self, arrays: dict, names=MUTATED_FIELDS):
         names = FIELD_NAMES if names is None else names
         st = _arrays_struct(arrays, names, self.shape_args)
@@ -219,6 +259,13 @@ class Caar:
     # -- the hot path -------------------------------------------------------------------------------
     def compute_and_apply_rhs(self, nsteps=1, mode=MODE_FAST, sync=True):
         _check(self.lib, self.lib.caar_run(self.h, C.byref(self.control), nsteps, mode), "caar_run")
+        if sync:
+            self.sync()
+
+    def run_stepping(self, nsteps, mode=MODE_FAST, sync=True):
+        """nsteps evaluations with TestData::update_time_levels (PO/data_structures.cpp:174-180) after each;
+        self.control holds the rotated time levels afterwards."""
+        _check(self.lib, self.lib.caar_run_stepping(self.h, C.byref(self.control), nsteps, mode), "caar_run_stepping")
         if sync:
             self.sync()
 

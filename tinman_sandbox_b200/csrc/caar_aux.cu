@@ -92,7 +92,66 @@ __global__ void __launch_bounds__(512) saxpby_kernel(double a, double b, double*
   if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) x[n - 1] = a * x[n - 1] + b * y[n - 1];
 }
 
+// ---- host-layout conversion for the Fortran (F90 flat pointer) boundary --------------------------------------
+// The reference's C++ arrays are row-major [igp][jgp]([comp]) with C [igp][jgp] == Fortran (i,j) index for index
+// (PO/test_macros.hpp), i.e. the Fortran arrays of F/element_state_mod.F90:17-23 / F/element_mod.F90:69-121, whose
+// memory order is first-index-fastest, hold every 4x4 block transposed, the (u,v) component as a slower
+// dimension (v(np,np,2,nlev,tl)) and the 2x2 tensor indices slowest (D(np,np,2,2)) — the order HOMMEXX reads its
+// F90 pointers in (LV/Elements.cpp:48-99,164-292). Per block of B doubles (16 scalar, 32 vector, 64 tensor):
+//   scalar  cxx[i*4+j]               <-> f90[j*4+i]
+//   vector  cxx[(i*4+j)*2+c]         <-> f90[c*16+j*4+i]
+//   tensor  cxx[((i*4+j)*2+a)*2+b]   <-> f90[(b*2+a)*16+j*4+i]
+// Tracers: cxx blocks [iq][qni][lev] <-> f90 blocks [qni][iq][lev] (Qdp(np,np,nlev,qsize_d,2)).
+__device__ __forceinline__ int f90_index(int kind, int q) {
+  if (kind == 0) return (q & 3) * 4 + (q >> 2);
+  if (kind == 1) return (q & 1) * 16 + ((q >> 1) & 3) * 4 + (q >> 3);
+  return ((q & 1) * 2 + ((q >> 1) & 1)) * 16 + ((q >> 2) & 3) * 4 + (q >> 4);
+}
+
+// cxx and f90 point at block 0 of the same chunk; blk0 = index of that block in the whole field (tracer remap)
+__global__ void __launch_bounds__(256) relayout_kernel(double* __restrict__ cxx, double* __restrict__ f90, size_t nblocks,
+                                                        int kind, int to_cxx, int q_dim, int nlev, size_t blk0) {
+  const int B = 16 << kind;
+  const size_t n = nblocks * B;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t blk = g >> (4 + kind);
+    const int q = (int)(g & (B - 1));
+    size_t fblk = blk;
+    if (q_dim > 1) {  // tracer block order: cxx [e][iq][qni][lev] -> f90 [e][qni][iq][lev]
+      const size_t gb = blk0 + blk;
+      const size_t lev = gb % nlev, qni = (gb / nlev) % 2, iq = (gb / nlev / 2) % q_dim, e = gb / nlev / 2 / q_dim;
+      fblk = ((e * 2 + qni) * q_dim + iq) * nlev + lev - blk0;  // relative to the same chunk origin (chunks are whole elements)
+    }
+    double* c = cxx + g;
+    double* f = f90 + fblk * B + f90_index(kind, q);
+    if (to_cxx) *c = *f; else *f = *c;
+  }
+}
+
+__global__ void __launch_bounds__(256) reciprocal_kernel(double* __restrict__ out, const double* __restrict__ in, size_t n) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (size_t)gridDim.x * blockDim.x)
+    out[g] = __ddiv_rn(1.0, in[g]);
+}
+
 }  // namespace
+
+cudaError_t launch_relayout(double* cxx, double* f90, size_t nblocks, int kind, bool to_cxx, int q_dim, int nlev,
+                            size_t blk0, cudaStream_t s) {
+  if (nblocks == 0) return cudaSuccess;
+  const size_t n = nblocks * (16u << kind);
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  relayout_kernel<<<(unsigned)blocks, 256, 0, s>>>(cxx, f90, nblocks, kind, to_cxx ? 1 : 0, q_dim, nlev, blk0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reciprocal(double* out, const double* in, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  reciprocal_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, in, n);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_norms(const KernelArgs& a, int tl, int nets, int nete, double* partial, double* out3,
                          cudaStream_t s) {

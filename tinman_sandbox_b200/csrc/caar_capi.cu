@@ -72,6 +72,7 @@ struct caar_handle_s {
   int n_chunk_ev;
   cudaEvent_t ev_fence;
   // caar_run_host zero-copy path: TMA descriptors over the caller's mapped host arrays, rebuilt when they move
+  double* stage;  // device staging buffer of the Fortran-layout copies (allocated on first use)
   caar::TmaMaps* tma_host;
   double* tma_host_key[CAAR_NUM_FIELDS];
 };
@@ -211,6 +212,7 @@ int caar_destroy(caar_handle h) {
     if (h->dev[f]) cudaFree(h->dev[f]);
   if (h->partial) cudaFree(h->partial);
   if (h->out3) cudaFree(h->out3);
+  if (h->stage) cudaFree(h->stage);
   if (h->out3_host) cudaFreeHost(h->out3_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -261,6 +263,78 @@ static int copy_fields(caar_handle h, const caar_arrays* host, unsigned mask, bo
 
 int caar_upload(caar_handle h, const caar_arrays* host, unsigned mask) { return copy_fields(h, host, mask, true); }
 int caar_download(caar_handle h, const caar_arrays* host, unsigned mask) { return copy_fields(h, host, mask, false); }
+
+// ---- Fortran (F90 flat pointer) host layout: copies go through a device staging buffer and a relayout kernel
+static const size_t kStageBytes = (size_t)256 << 20;
+
+// block kind of a field for the relayout kernel: 0 = 4x4 scalars, 1 = (u,v) per level, 2 = 2x2 tensors
+static int field_kind(int f) { return (f == 0 || f == 1) ? 2 : (f == 7 || f == 15) ? 1 : 0; }
+
+static int copy_fields_f90(caar_handle h, const caar_arrays* host, unsigned mask, bool to_device) {
+  if (!h || !host) return fail(CAAR_ERR_INVALID, "null argument");
+  DeviceGuard guard(h->device);
+  double* const* tab = as_table(host);
+  const caar_dims& d = h->dims;
+  if (!h->stage) CU_TRY(cudaMalloc(&h->stage, kStageBytes));
+  for (int f = 0; f < CAAR_NUM_FIELDS; ++f) {
+    if (!(mask & (1u << f))) continue;
+    const size_t per_elem = field_count(d, f) / d.nelem;  // doubles
+    if (f == 5 && !tab[f] && to_device) {  // HOMMEXX passes no rmetdet (LV/Elements.hpp:92): rmetdet = 1/metdet
+      if (!(mask & CAAR_F_METDET) || !tab[4])
+        return fail(CAAR_ERR_INVALID, "rmetdet is null: metdet must be uploaded in the same call");
+      continue;  // filled after the loop
+    }
+    if (!tab[f]) return fail(CAAR_ERR_INVALID, "host pointer of field %d is null", f);
+    const int kind = field_kind(f);
+    const size_t blocks_per_elem = per_elem / (16u << kind);
+    size_t chunk = kStageBytes / (per_elem * sizeof(double));
+    if (chunk < 1) return fail(CAAR_ERR_UNSUPPORTED, "field %d: one element exceeds the staging buffer", f);
+    const int q_dim = (f == 10) ? d.qsize_d : 1;
+    for (size_t e0 = 0; e0 < (size_t)d.nelem; e0 += chunk) {
+      const size_t ne = ((size_t)d.nelem - e0 < chunk) ? (size_t)d.nelem - e0 : chunk;
+      const size_t bytes = ne * per_elem * sizeof(double);
+      double* dev = h->dev[f] + e0 * per_elem;
+      double* hst = tab[f] + e0 * per_elem;
+      if (to_device) {
+        CU_TRY(cudaMemcpyAsync(h->stage, hst, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(caar::launch_relayout(dev, h->stage, ne * blocks_per_elem, kind, true, q_dim, d.nlev,
+                                     e0 * blocks_per_elem, h->stream));
+      } else {
+        CU_TRY(caar::launch_relayout(dev, h->stage, ne * blocks_per_elem, kind, false, q_dim, d.nlev,
+                                     e0 * blocks_per_elem, h->stream));
+        CU_TRY(cudaMemcpyAsync(hst, h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+      }
+      ++h->launches;
+    }
+  }
+  if (to_device && (mask & CAAR_F_RMETDET) && !tab[5]) {
+    CU_TRY(caar::launch_reciprocal(h->dev[5], h->dev[4], field_count(d, 5), h->stream));
+    ++h->launches;
+  }
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return CAAR_OK;
+}
+
+int caar_upload_layout(caar_handle h, const caar_arrays* host, unsigned mask, int layout) {
+  if (layout == CAAR_LAYOUT_CXX) return copy_fields(h, host, mask, true);
+  if (layout == CAAR_LAYOUT_F90) return copy_fields_f90(h, host, mask, true);
+  return fail(CAAR_ERR_INVALID, "layout=%d", layout);
+}
+
+int caar_download_layout(caar_handle h, const caar_arrays* host, unsigned mask, int layout) {
+  if (layout == CAAR_LAYOUT_CXX) return copy_fields(h, host, mask, false);
+  if (layout == CAAR_LAYOUT_F90) return copy_fields_f90(h, host, mask, false);
+  return fail(CAAR_ERR_INVALID, "layout=%d", layout);
+}
+
+int caar_set_params_f90(caar_handle h, const caar_constants* c, const double dvv_f90[16], double ps0,
+                        const double* hyai) {
+  if (!dvv_f90) return fail(CAAR_ERR_INVALID, "null argument");
+  double dvv[16];  // Fortran Dvv(i,j) is stored j-major; the C++ side indexes Dvv[i][j] (F/main.F90:94)
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) dvv[i * 4 + j] = dvv_f90[j * 4 + i];
+  return caar_set_params(h, c, dvv, ps0, hyai);
+}
 
 int caar_host_register(void* ptr, size_t bytes) {
   if (!ptr || !bytes) return fail(CAAR_ERR_INVALID, "null argument");
@@ -496,6 +570,24 @@ int caar_host_traffic(caar_handle h, const caar_control* ctl, int mode, size_t* 
   const size_t n = (size_t)(ctl->nete - ctl->nets);
   *h2d_bytes = in * n * sizeof(double);
   *d2h_bytes = out * n * sizeof(double);
+  return CAAR_OK;
+}
+
+void caar_update_time_levels(caar_control* ctl) {
+  if (!ctl) return;
+  const int tmp = ctl->np1;  // TestData::update_time_levels, PO/data_structures.cpp:174-180
+  ctl->np1 = ctl->nm1;
+  ctl->nm1 = ctl->n0;
+  ctl->n0 = tmp;
+}
+
+int caar_run_stepping(caar_handle h, caar_control* ctl, int nsteps, int mode) {
+  if (!ctl) return fail(CAAR_ERR_INVALID, "control is null");
+  if (nsteps < 0) return fail(CAAR_ERR_INVALID, "nsteps=%d", nsteps);
+  for (int s = 0; s < nsteps; ++s) {
+    if (int rc = caar_run(h, ctl, 1, mode)) return rc;
+    caar_update_time_levels(ctl);
+  }
   return CAAR_OK;
 }
 

@@ -66,6 +66,10 @@ size_t strict_smem_bytes(int nlev);
 
 cudaError_t launch_norms(const KernelArgs& a, int tl, int nets, int nete, double* partial /*[nelem][3]*/,
                          double* out3, cudaStream_t s);
+// host-layout conversion (Fortran boundary): kind 0 = 4x4 scalar blocks, 1 = (u,v) level blocks, 2 = 2x2 tensors
+cudaError_t launch_relayout(double* cxx, double* f90, size_t nblocks, int kind, bool to_cxx, int q_dim, int nlev,
+                            size_t blk0, cudaStream_t s);
+cudaError_t launch_reciprocal(double* out, const double* in, size_t n, cudaStream_t s);
 cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t n, cudaStream_t s);
 
 }  // namespace caar

@@ -74,6 +74,31 @@ __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// ---- thread-block cluster primitives (CL = 2: the two halves of an element's column run as a CTA pair) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Store a row into the same shared-memory location of CTA `rank` of this cluster (distributed shared memory) and
+// credit its 32 bytes to that CTA's mbarrier `bar`: the receiver just waits on its own mbarrier — no cluster
+// barrier, no fence on the sender (st.async ... mbarrier::complete_tx::bytes).
+__device__ __forceinline__ void st_row_async_remote(const double* local, const uint64_t* bar, uint32_t rank,
+                                                    const double (&x)[4]) {
+  uint32_t dst, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst),
+               "d"(x[0]), "d"(x[1]), "r"(rbar)
+               : "memory");
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst + 16),
+               "d"(x[2]), "d"(x[3]), "r"(rbar)
+               : "memory");
+}
+
 // 1/x to ~1 ulp: hardware 20-bit seed + two Newton steps (x is a positive, normal pressure / thickness)
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
@@ -206,13 +231,23 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
   return v;
 }
 
+#ifndef CAAR_CL128
+#define CAAR_CL128 2  // nlev = 128: the column is split over a cluster of two 256-thread CTAs
+#endif
 #ifndef CAAR_REGS_SMALL
 #define CAAR_REGS_SMALL 96  // 2 CTAs of 9 warps per SM = 5 warps on the fullest SMSP: 16384/(5*32) = 102 -> 96
 #endif
 
-template <int L>
+// register budget per thread for a CTA of `threads` threads: two CTAs per SM where the register file allows it
+constexpr int regs_for(int threads) {
+  return threads <= 256 ? 128                // 2 x 256 x 128 = the whole 64K-register file
+         : threads <= 320 ? CAAR_REGS_SMALL  // 2 x 288 threads (nlev = 72)
+                          : 128;             // one 512-thread CTA per SM
+}
+
+template <int L, int NWT>  // L = levels held by this CTA, NWT = warps per element (scan totals of the whole column)
 struct Smem {
-  static constexpr int LF = L * PTS;  // doubles per scalar level-field
+  static constexpr int LF = L * PTS;  // doubles per scalar level-field (this CTA's slab)
   // late inputs, overwritten in place by the outputs of the same shape
   double vn0[2 * LF];      // derived_vn0           -> derived_vn0
   double vm1[2 * LF];      // v(nm1)                -> v(np1)
@@ -222,72 +257,105 @@ struct Smem {
   double Tm1[LF];          // T(nm1)                -> T(np1)
   double Tn0[LF];          // T(n0)   (input only: keeps 8 registers free during the grad-p peak)
   double Qd[LF];           // Qdp     (input only)
-  double tot[3][L / 8][16];
+  double tot[3][NWT][16];
   // 2x2 tensors: [igp] stride GS = 20 doubles (160 B) instead of 16 so that the four rows read by the
   // four igp-lanes of a level fall into different banks (conflict-free 128-bit broadcast loads)
   double dinv[4 * 20];     // Dinv * rrearth, [igp][jgp][2][2]
   double dmat[4 * 20];     // D
   double met[16], rmet[16], fcor[16], mp[16], phis[16];
   uint64_t bar[3];
+  uint64_t xbar[3];  // CL = 2: arrival of the peer CTA's scan totals tot[0], tot[1], tot[2]
 };
 
-template <int L>
-__global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_SMALL : 128) caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ TmaMaps M) {
-  constexpr int NW = L / 8;
-  constexpr int LF = L * PTS;
+// L = levels of the element, CL = CTAs per element (a thread-block cluster of CL CTAs, each holding L/CL levels).
+// CL = 2 is used for nlev = 128: two 256-thread CTAs at 128 registers instead of one 512-thread CTA, so that two
+// CTAs (of different elements, in different phases) share an SM; the vertical scans exchange their per-warp
+// totals through distributed shared memory and a cluster barrier.
+template <int L, int CL>
+__global__ void __launch_bounds__(4 * L / CL) __maxnreg__(regs_for(4 * L / CL))
+caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ TmaMaps M) {
+  constexpr int LC = L / CL;        // levels per CTA
+  constexpr int NW = LC / 8;        // warps per CTA
+  constexpr int NWT = L / 8;        // warps per element
+  constexpr int LF = LC * PTS;      // doubles per scalar level-field slab of this CTA
+  constexpr int LFE = L * PTS;      // ... of the whole element
   constexpr int GS = 20;  // padded igp stride of the 2x2 tensors in shared memory
-  constexpr unsigned FB = LF * sizeof(double);  // bytes of one scalar level-field of one element
+  constexpr unsigned FB = LF * sizeof(double);  // bytes of one scalar level-field slab
+  static_assert(L % (8 * CL) == 0, "a warp holds 8 levels");
   extern __shared__ unsigned char smem_raw[];
   // swizzled TMA tiles need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
-  Smem<L>& S = *reinterpret_cast<Smem<L>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  Smem<LC, NWT>& S = *reinterpret_cast<Smem<LC, NWT>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int t = threadIdx.x;
   const int lane = t & 31, w = t >> 5;
   const int r = t & 3;  // igp
-  const size_t e = (size_t)(A.nets + blockIdx.x);
-  const size_t lf = LF;
-  const int off = t * 4;  // this thread's 4 points inside a scalar level-field
+  const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int gw = (int)rank * NW + w;  // warp index within the element's column
+  const int lev0 = (int)rank * LC;    // first level of this CTA
+  const int ie = A.nets + (int)(blockIdx.x / CL);
+  const size_t e = (size_t)ie;
+  const size_t lf = LFE;
+  const int off = lev0 * PTS + t * 4;  // this thread's 4 points inside a scalar level-field of the element
   // this thread's first 16-byte chunk inside a swizzled scalar tile (row = level) / (u,v) tile (row = t/2)
   const uint32_t sw1 = (uint32_t)(t >> 2) * 128u + ((uint32_t)((2 * r) ^ ((t >> 2) & 7)) << 4);
   const uint32_t sw2 = (uint32_t)(t >> 1) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((t >> 1) & 7)) << 4);
-  const int ie = A.nets + (int)blockIdx.x;
-  const int row_nm1 = (ie * A.ntl + A.nm1) * L, row_np1 = (ie * A.ntl + A.np1) * L;
+  const int row_nm1 = (ie * A.ntl + A.nm1) * L + lev0, row_np1 = (ie * A.ntl + A.np1) * L + lev0;
+  const int row_e = ie * L + lev0;  // first row of this CTA in the [E][L] arrays
 
   // ---- kernel entry: one thread starts the TMA prefetch of the late inputs
   if (t == 0) {
     mbar_init(&S.bar[0], 1);
     mbar_init(&S.bar[1], 1);
     mbar_init(&S.bar[2], 1);
+    if (CL > 1) {
+      // the column is split over two CTAs: rank 1 receives rank 0's forward totals (pressure, divergence), rank 0
+      // receives rank 1's reverse totals (geopotential): NW rows of 128 B each
+      constexpr unsigned XB = NW * 16 * sizeof(double);
+      mbar_init(&S.xbar[0], 1);
+      mbar_init(&S.xbar[1], 1);
+      mbar_init(&S.xbar[2], 1);
+      fence_mbar_init_cluster();
+      if (rank == 1) {
+        mbar_expect_tx(&S.xbar[0], XB);
+        mbar_expect_tx(&S.xbar[2], XB);
+      } else {
+        mbar_expect_tx(&S.xbar[1], XB);
+      }
+    }
     fence_proxy_async();
     mbar_expect_tx(&S.bar[2], (A.qn0 != -1 ? 2 : 1) * FB);
-    tma_load(S.Tn0, &M.T, (ie * A.ntl + A.n0) * L, &S.bar[2]);
-    if (A.qn0 != -1) tma_load(S.Qd, &M.Qdp, ((ie * A.qsize_d + 0) * 2 + A.qn0) * L, &S.bar[2]);
+    tma_load(S.Tn0, &M.T, (ie * A.ntl + A.n0) * L + lev0, &S.bar[2]);
+    if (A.qn0 != -1) tma_load(S.Qd, &M.Qdp, ((ie * A.qsize_d + 0) * 2 + A.qn0) * L + lev0, &S.bar[2]);
     mbar_expect_tx(&S.bar[0], 4 * FB);
-    tma_load(S.vn0, &M.vn0, ie * 2 * L, &S.bar[0]);
+    tma_load(S.vn0, &M.vn0, row_e * 2, &S.bar[0]);
     tma_load(S.dpm, &M.dp3d, row_nm1, &S.bar[0]);
-    tma_load(S.pec, &M.pecnd, ie * L, &S.bar[0]);
+    tma_load(S.pec, &M.pecnd, row_e, &S.bar[0]);
     mbar_expect_tx(&S.bar[1], 4 * FB);
-    tma_load(S.omp, &M.omega_p, ie * L, &S.bar[1]);
+    tma_load(S.omp, &M.omega_p, row_e, &S.bar[1]);
     tma_load(S.Tm1, &M.T, row_nm1, &S.bar[1]);
     tma_load(S.vm1, &M.v, row_nm1 * 2, &S.bar[1]);
     // pull the early inputs and the geometry of a later element (the one expected to run next on this SM slot) into L2, so
     // that its kernel-start loads see L2 latency instead of DRAM latency
     const int pe = ie + A.pf_dist;
     if (A.pf_dist > 0 && pe < A.nete) {
-      const size_t pn0 = ((size_t)pe * A.ntl + A.n0) * lf;
+      const size_t pn0 = ((size_t)pe * A.ntl + A.n0) * lf + (size_t)lev0 * PTS;
       prefetch_l2(A.dp3d + pn0, FB);
       prefetch_l2(A.v + pn0 * 2, 2 * FB);
       prefetch_l2(A.T + pn0, FB);
-      if (A.qn0 != -1) prefetch_l2(A.Qdp + (((size_t)pe * A.qsize_d + 0) * 2 + A.qn0) * lf, FB);
-      prefetch_l2(A.Dinv + (size_t)pe * 64, 512);
-      prefetch_l2(A.D + (size_t)pe * 64, 512);
-      prefetch_l2(A.metdet + (size_t)pe * 16, 128);
-      prefetch_l2(A.rmetdet + (size_t)pe * 16, 128);
-      prefetch_l2(A.fcor + (size_t)pe * 16, 128);
-      prefetch_l2(A.spheremp + (size_t)pe * 16, 128);
-      prefetch_l2(A.phis + (size_t)pe * 16, 128);
+      if (A.qn0 != -1) prefetch_l2(A.Qdp + (((size_t)pe * A.qsize_d + 0) * 2 + A.qn0) * lf + (size_t)lev0 * PTS, FB);
+      if (rank == 0) {
+        prefetch_l2(A.Dinv + (size_t)pe * 64, 512);
+        prefetch_l2(A.D + (size_t)pe * 64, 512);
+        prefetch_l2(A.metdet + (size_t)pe * 16, 128);
+        prefetch_l2(A.rmetdet + (size_t)pe * 16, 128);
+        prefetch_l2(A.fcor + (size_t)pe * 16, 128);
+        prefetch_l2(A.spheremp + (size_t)pe * 16, 128);
+        prefetch_l2(A.phis + (size_t)pe * 16, 128);
+      }
     }
   }
+
+  if (CL > 1) cluster_arrive();  // "my mbarriers are initialised" — the peer may send to me once it has waited on this
 
   // ---- early inputs straight to registers
   const size_t on0 = (e * A.ntl + A.n0) * lf + off;
@@ -326,12 +394,17 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
     Row p;
 #pragma unroll
     for (int j = 0; j < 4; ++j) p.x[j] = scan_down(dp.x[j], lane);
-    if (lane >= 28) st_row(&S.tot[0][w][r * 4], p);
+    if (CL > 1) cluster_wait();  // the peer CTA is running and has initialised its mbarriers
+    if (lane >= 28) {
+      st_row(&S.tot[0][gw][r * 4], p);
+      if (CL > 1 && rank == 0) st_row_async_remote(&S.tot[0][gw][r * 4], &S.xbar[0], 1u, p.x);
+    }
     __syncthreads();  // (1) tot[0], geometry, mbarrier init visible
+    if (CL > 1 && rank == 1) mbar_wait(&S.xbar[0], 0);  // rank 0's totals have landed
     double carry[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int ww = 0; ww < NW - 1; ++ww)
-      if (ww < w) {
+    for (int ww = 0; ww < NWT - 1; ++ww)
+      if (ww < gw) {
         const Row c = ld_row(&S.tot[0][ww][r * 4]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) carry[j] += c.x[j];
@@ -469,8 +542,14 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
         dp.x[j] = sq;      // reuse: warp totals live in the end lanes
         divdp.x[j] = sd;
       }
-      if (lane < 4) st_row(&S.tot[1][w][r * 4], dp);
-      if (lane >= 28) st_row(&S.tot[2][w][r * 4], divdp);
+      if (lane < 4) {
+        st_row(&S.tot[1][gw][r * 4], dp);
+        if (CL > 1 && rank == 1) st_row_async_remote(&S.tot[1][gw][r * 4], &S.xbar[1], 0u, dp.x);
+      }
+      if (lane >= 28) {
+        st_row(&S.tot[2][gw][r * 4], divdp);
+        if (CL > 1 && rank == 0) st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[2], 1u, divdp.x);
+      }
     }
     // T tendency with the omega carry factored out: ttens = kappa*T_v*omega - v.gradT, omega = a - rp*carry
     Row tta, ttb;
@@ -481,20 +560,21 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
       ttb.x[j] = kt * rp.x[j];
     }
     __syncthreads();  // (2) scan totals visible; vn0 / dp3d(np1) tiles complete
+    if (CL > 1) mbar_wait(&S.xbar[rank == 0 ? 1 : 2], 0);  // the peer's totals have landed
     if (t == 0) {
-      tma_store(&M.vn0, ie * 2 * L, S.vn0);
+      tma_store(&M.vn0, row_e * 2, S.vn0);
       tma_store(&M.dp3d, row_np1, S.dpm);
       bulk_commit();
     }
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int ww = 0; ww < NW; ++ww) {
-      if (ww > w) {
+    for (int ww = 0; ww < NWT; ++ww) {
+      if (ww > gw) {
         const Row c = ld_row(&S.tot[1][ww][r * 4]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) cq[j] += c.x[j];
       }
-      if (ww < w) {
+      if (ww < gw) {
         const Row c = ld_row(&S.tot[2][ww][r * 4]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) cd[j] += c.x[j];
@@ -539,30 +619,41 @@ __global__ void __launch_bounds__(4 * L) __maxnreg__((4 * L <= 320) ? CAAR_REGS_
   fence_proxy_async();
   __syncthreads();  // (3) all output tiles complete
   if (t == 0) {
-    tma_store(&M.omega_p, ie * L, S.omp);
+    tma_store(&M.omega_p, row_e, S.omp);
     tma_store(&M.T, row_np1, S.Tm1);
-    tma_store(&M.phi, ie * L, S.pec);
+    tma_store(&M.phi, row_e, S.pec);
     tma_store(&M.v, row_np1 * 2, S.vm1);
     bulk_commit();
     bulk_wait_read_all();  // shared memory must stay alive until the TMA engine has read it
   }
 }
 
-template <int L>
+template <int L, int CL>
 cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   const int n = a.nete - a.nets;
   if (n <= 0) return cudaSuccess;
+  constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8>) + 1024;
   // per device (function attributes are per context): cheap enough to set on every launch
-  cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(Smem<L>) + 1024);
+  cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) return e;
-  // ask for the largest shared-memory carveout so that two 79 KB CTAs are resident per SM
-  e = cudaFuncSetAttribute(caar_fused_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  // ask for the largest shared-memory carveout so that two ~80 KB CTAs are resident per SM
+  e = cudaFuncSetAttribute(caar_fused_kernel<L, CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   if (!a.tma) return cudaErrorInvalidValue;
-  caar_fused_kernel<L><<<n, 4 * L, sizeof(Smem<L>) + 1024, s>>>(a, *static_cast<const TmaMaps*>(a.tma));
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n * CL, 1, 1);
+  cfg.blockDim = dim3(4 * L / CL, 1, 1);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CL > 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, caar_fused_kernel<L, CL>, a, *static_cast<const TmaMaps*>(a.tma));
 }
 
 }  // namespace
@@ -580,16 +671,17 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   }
   const encode_t encode = reinterpret_cast<encode_t>(fn);
   const cuuint64_t E = (cuuint64_t)a.nelem, L = (cuuint64_t)a.nlev, ntl = (cuuint64_t)a.ntl;
+  const cuuint32_t LB = (cuuint32_t)(a.nlev == 128 ? a.nlev / CAAR_CL128 : a.nlev);  // levels per CTA = box rows
   struct Spec { CUtensorMap* m; const void* base; cuuint64_t rows; cuuint32_t box; const char* name; };
   const Spec specs[8] = {
-      {&out->Qdp, a.Qdp, E * (cuuint64_t)a.qsize_d * 2 * L, (cuuint32_t)L, "Qdp"},
-      {&out->dp3d, a.dp3d, E * ntl * L, (cuuint32_t)L, "dp3d"},
-      {&out->T, a.T, E * ntl * L, (cuuint32_t)L, "T"},
-      {&out->v, a.v, E * ntl * L * 2, (cuuint32_t)(2 * L), "v"},
-      {&out->vn0, a.vn0, E * L * 2, (cuuint32_t)(2 * L), "vn0"},
-      {&out->pecnd, a.pecnd, E * L, (cuuint32_t)L, "pecnd"},
-      {&out->omega_p, a.omega_p, E * L, (cuuint32_t)L, "omega_p"},
-      {&out->phi, a.phi, E * L, (cuuint32_t)L, "phi"},
+      {&out->Qdp, a.Qdp, E * (cuuint64_t)a.qsize_d * 2 * L, LB, "Qdp"},
+      {&out->dp3d, a.dp3d, E * ntl * L, LB, "dp3d"},
+      {&out->T, a.T, E * ntl * L, LB, "T"},
+      {&out->v, a.v, E * ntl * L * 2, 2 * LB, "v"},
+      {&out->vn0, a.vn0, E * L * 2, 2 * LB, "vn0"},
+      {&out->pecnd, a.pecnd, E * L, LB, "pecnd"},
+      {&out->omega_p, a.omega_p, E * L, LB, "omega_p"},
+      {&out->phi, a.phi, E * L, LB, "phi"},
   };
   for (const Spec& sp : specs) {
     const cuuint64_t gdim[2] = {16, sp.rows};
@@ -620,11 +712,13 @@ cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
     const char* v = getenv("CAAR_PF_DIST");
     return v ? atoi(v) : -1;
   }();
-  // default distance 148 elements (one CTA per SM ahead): best of a 0/74/148/296/592 sweep at ne=120
-  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : 148);
+  // default distance: nlev=72 -> 148 elements (one CTA per SM ahead; best of an 8...592 sweep at ne=120: 90 % of
+  // the measured peak vs 83 % at 16); nlev=128 (CTA pairs) -> 16 (flat optimum 4...24: 82 %, 74 % at 148).
+  // Sweeps: profiles/README.md.
+  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : (a.nlev == 128 ? 16 : 148));
   switch (a.nlev) {
-    case 72: return launch_L<72>(a, s);
-    case 128: return launch_L<128>(a, s);
+    case 72: return launch_L<72, 1>(a, s);
+    case 128: return launch_L<128, CAAR_CL128>(a, s);
   }
   return launch_fused_ldg(a, s);
 }
