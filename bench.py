@@ -64,53 +64,66 @@ def ncu_traffic_per_launch(nelem, nlev):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe) through NVML
+    (the library behind nvidia-smi) from a background thread every few milliseconds — the timed region of the
+    default run lasts ~60 ms, too short for `nvidia-smi -lms`."""
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, gpu_index, period_s=0.004):
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain list of ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = gpu_index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[gpu_index])
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self.nv = None
+            return
+        self.period = period_s
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        nv = self.nv
+        names = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                 ("sw_power_cap", 0x4))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get(self.dev))
+                for n, bit in names:
+                    if r & bit:
+                        self.reasons.add(n)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region."""
+        self.t_mark = len(self.samples)
+        self.reasons.clear()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._thread is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        self.f.close()
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+        self._stop.set()
+        self._thread.join(timeout=2)
+        sm = self.samples[getattr(self, "t_mark", 0):]
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), reasons=sorted(self.reasons), samples=len(sm),
+                       power_w_max=max(self.power) if self.power else None)
         return out
 
 
@@ -235,6 +248,17 @@ def main():
         pinned.append(t)
         return t.numpy().reshape(shape)
 
+    # page-locking world x 16 GB must not exhaust the box: fall back to pageable host arrays (and say so) if it would
+    try:
+        import psutil
+        host_total = psutil.virtual_memory().total
+    except Exception:
+        host_total = 0
+    host_need = world * E * (186112.0 / 72 * L)
+    pin_ok = host_total == 0 or host_need < 0.6 * host_total
+    if not pin_ok:
+        def alloc(shape):  # noqa: F811
+            return np.zeros(shape, dtype=np.float64)
     td = TestData(E, L, alloc=alloc).init_data(elem_offset=rank * E)
     h = tb.Caar(E, L, device=local_rank)
     h.set_params(td.consts, td.dvv, td.ps0, td.hyai)
@@ -245,6 +269,10 @@ def main():
     h.compute_and_apply_rhs(args.warmup, mode)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    h.compute_and_apply_rhs(2, mode)       # the sampler thread is running: put the GPU under load, then mark
+    barrier()
+    if sampler:
+        sampler.mark()
     launches0 = h.launch_count()
     h.timer_start()
     h.compute_and_apply_rhs(args.steps, mode, sync=False)
@@ -286,8 +314,9 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * dt / args.e2e_steps,
                "pcie_gbs": {"h2d": h2d * args.e2e_steps / dt / 1e9, "d2h": d2h * args.e2e_steps / dt / 1e9},
-               "how": "caar_run_host per step: host arrays in, host arrays out (pinned), copy-in | kernel | "
-                      "copy-out pipelined over element chunks; PCIe-bound"}
+               "how": "caar_run_host per step: host arrays in, host arrays out (%s), copy-in | kernel | "
+                      "copy-out pipelined over element chunks; PCIe-bound" %
+                      ("pinned" if pin_ok else "PAGEABLE: pinning would take >60% of host RAM")}
     h.close()
 
     # ---- roofline of the dominant (only) kernel of a step
