@@ -127,6 +127,29 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs NVML reports as local to its GPU BEFORE the host arrays are allocated and
+    first touched, so that the page-locked arrays of the end-to-end leg live on the GPU's NUMA node (what a
+    launcher would do with numactl). Returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = gpu_index
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            phys = int(vis.split(",")[gpu_index])
+        dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(dev, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -223,6 +246,8 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -330,6 +355,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)       # the CPU baseline uses every host core, not only the GPU's node
         rate, kind, cores, sample, _ = cpu_reference_rate(L, target_s=args.cpu_target_s)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
@@ -340,7 +366,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference closed-form init)",
             "config": {"workload": f"ne=120 cubed sphere: {E} elements per GPU, np=4, nlev={L}, FP64, "
                                    f"n0/np1/nm1 distinct, qn0=0",
-                       "elements_per_gpu": E, "nlev": L, "mode": args.mode,
+                       "elements_per_gpu": E, "nlev": L, "mode": args.mode, "host_cpus_bound": numa,
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" %
                              (sum(a.nbytes for a in td.arrays.values()) / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,
