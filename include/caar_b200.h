@@ -216,6 +216,22 @@ long long caar_launch_count(caar_handle h);
 int caar_timer_start(caar_handle h);
 int caar_timer_stop(caar_handle h, float* ms);
 
+/* ---- the step after CAAR: tracer advection RHS ----
+   qtens[ie][iq][k] = Qdp[ie][iq][qn0][k] - dt * divergence_sphere(vstar[ie][k] * Qdp[ie][iq][qn0][k]) for tracers
+   iq < qsize, every level, elements [nets,nete): EulerStepFunctor::operator() (LV/EulerStepFunctor.hpp:33-66) =
+   divergence_sphere_update(alpha=-dt, beta=1) (LV/SphereOperators.hpp:362-403) with the reference's
+   divergence_sphere (PO/sphere_operators.cpp:50-89). Uses the handle's Dinv/metdet/rmetdet/Qdp mirrors, Dvv and
+   rrearth, plus two arrays that struct Arrays does not hold, owned by the handle and moved with
+   caar_extra_upload/download in the pointers_only conventions:
+     CAAR_X_VSTAR  vstar [E][L][4][4][2]        (derived%vstar(np,np,2,nlev), F/element_mod.F90:70; input)
+     CAAR_X_QTENS  qtens [E][qsize_d][L][4][4]  (buffers.qtens, LV/Elements.hpp:71; output)
+   Asynchronous on the handle's stream (caar_sync / caar_extra_download wait). mode as in caar_run. */
+enum { CAAR_X_VSTAR = 0, CAAR_X_QTENS = 1 };
+size_t caar_extra_count(const caar_dims* dims, int which);
+int caar_extra_upload(caar_handle h, int which, const double* host);
+int caar_extra_download(caar_handle h, int which, double* host);
+int caar_euler_step(caar_handle h, int nets, int nete, int qn0, int qsize, double dt, int mode);
+
 /* Sum of squares of v, T, dp3d at time level `tl` over elements [nets,nete) — the three quantities
    print_results_2norm takes the sqrt of (PO/compute_and_apply_rhs.cpp:384-398). Returned as SUMS OF
    SQUARES so that ranks can all-reduce them before the sqrt. Synchronous. */

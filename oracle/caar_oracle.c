@@ -389,6 +389,51 @@ void caar_oracle_norms(int nlev, int ntl, double* const* arrays, int nets, int n
   out[2] = sqrt(dn);
 }
 
+/* ---- tracer step after CAAR ---------------------------------------
+ * qtens[ie][iq][k] = Qdp[ie][iq][qn0][k] - dt * divergence_sphere(vstar[ie][k] * Qdp[ie][iq][qn0][k])
+ * Composition: level_vectorized_ppscan/EulerStepFunctor.hpp:33-66 (v_buf = vstar*qdp, q_buf = qdp, then
+ * divergence_sphere_update(alpha = -dt, beta = 1): q_buf = beta*q_buf + alpha*div(v_buf),
+ * level_vectorized_ppscan/SphereOperators.hpp:362-403). Operator: the reference's tested
+ * divergence_sphere, PO/sphere_operators.cpp:50-89 (div_sphere above, pinned bit-exactly to oracle/_ref).
+ * The reference never calls EulerStepFunctor from a driver and holds no known answers for it: the
+ * composition is pinned only by this restatement ("parity unpinned" for the composition, pinned for the
+ * operator). Layouts follow the pointers_only conventions: vstar [E][L][4][4][2] (as derived_vn0),
+ * qtens [E][qsize_d][L][4][4]. */
+void caar_oracle_divergence_sphere(const double* v, const double* dvv16, const double* dinv, const double* metdet,
+                                   const double* rmetdet, double rrearth, double* div) {
+  div_sphere(v, dvv16, dinv, metdet, rmetdet, rrearth, div);
+}
+
+void caar_oracle_euler_step(int nlev, int qsize_d, double* const* arrays, const double* vstar, double* qtens,
+                            int nets, int nete, int qn0, int qsize, double dt, const double* dvv16,
+                            double rrearth) {
+  const int L = nlev;
+  for (int ie = nets; ie < nete; ++ie) {
+    const double* dinv = arrays[F_DINV] + (size_t)ie * PTS * 4;
+    const double* metdet = arrays[F_METDET] + (size_t)ie * PTS;
+    const double* rmetdet = arrays[F_RMETDET] + (size_t)ie * PTS;
+    for (int iq = 0; iq < qsize; ++iq)
+      for (int k = 0; k < L; ++k) {
+        const double* q = arrays[F_QDP] + ((((size_t)ie * qsize_d + iq) * 2 + qn0) * L + k) * PTS;
+        const double* vs = vstar + ((size_t)ie * L + k) * PTS * 2;
+        double* out = qtens + (((size_t)ie * qsize_d + iq) * L + k) * PTS;
+        double vq[PTS * 2], div[PTS];
+        for (int n = 0; n < PTS; ++n) {
+          vq[2 * n] = vs[2 * n] * q[n];
+          vq[2 * n + 1] = vs[2 * n + 1] * q[n];
+        }
+        div_sphere(vq, dvv16, dinv, metdet, rmetdet, rrearth, div);
+        for (int n = 0; n < PTS; ++n) {
+          double t = q[n];
+          t *= 1.0;
+          t += (-dt) * div[n];
+          out[n] = t;
+        }
+      }
+  }
+}
+
+
 /* closed-form synthetic fields; 1-based index values as in the reference (PO/data_structures.cpp:38-92) */
 void caar_oracle_init(int E, int L, int Q, int ntl, double* const* a, int* ctl, double* dt2, double* k6,
                       double* dvv16, double* ps0, double* hyai) {

@@ -25,6 +25,17 @@ double caar_oracle_run(int nlev, int qsize_d, int ntl, double* const* arrays, co
 void caar_oracle_norms(int nlev, int ntl, double* const* arrays, int nets, int nete, int tl,
                        double out3[3]);
 
+/* one 4x4 level of the reference's divergence_sphere (PO/sphere_operators.cpp:50-89): v [4][4][2], dinv [4][4][2][2] */
+void caar_oracle_divergence_sphere(const double* v, const double* dvv16, const double* dinv, const double* metdet,
+                                   const double* rmetdet, double rrearth, double* div);
+
+/* tracer step after CAAR: qtens = Qdp(qn0) - dt*divergence_sphere(vstar*Qdp(qn0)) for tracers [0,qsize), every
+ * level, elements [nets,nete) (level_vectorized_ppscan/EulerStepFunctor.hpp:33-66).
+ * vstar [E][L][4][4][2], qtens [E][qsize_d][L][4][4] */
+void caar_oracle_euler_step(int nlev, int qsize_d, double* const* arrays, const double* vstar, double* qtens,
+                            int nets, int nete, int qn0, int qsize, double dt, const double* dvv16,
+                            double rrearth);
+
 /* x = a*x + b*y (saxpby_test/cxx/common.cpp:3-15), nthreads pthreads; returns wall seconds */
 double caar_oracle_saxpby(double a, double b, double* x, const double* y, size_t n, int sweeps,
                           int nthreads);

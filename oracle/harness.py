@@ -155,6 +155,22 @@ class PortOracle:
         self.lib.caar_oracle_norms(s.nlev, s.ntl, s.ptr_table(), int(s.ctl[0]), int(s.ctl[1]), tl, _dp(out))
         return out
 
+    def divergence_sphere(self, v, s: State, ie):
+        """One 4x4 level of PO divergence_sphere (sphere_operators.cpp:50-89): v (4,4,2) -> (4,4)."""
+        A = s.arrays
+        out = np.zeros((4, 4))
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        self.lib.caar_oracle_divergence_sphere(_dp(v), _dp(s.dvv), _dp(A["elem_Dinv"][ie]), _dp(A["elem_metdet"][ie]),
+                                               _dp(A["elem_rmetdet"][ie]), C.c_double(s.consts[0]), _dp(out))
+        return out
+
+    def euler_step(self, s: State, vstar, qtens, qn0, qsize, dt):
+        """qtens = Qdp(qn0) - dt*div(vstar*Qdp(qn0)) (level_vectorized_ppscan/EulerStepFunctor.hpp:33-66)."""
+        assert vstar.shape == (s.nelem, s.nlev, 4, 4, 2) and qtens.shape == (s.nelem, s.qsize_d, s.nlev, 4, 4)
+        self.lib.caar_oracle_euler_step(s.nlev, s.qsize_d, s.ptr_table(), _dp(vstar), _dp(qtens), int(s.ctl[0]),
+                                        int(s.ctl[1]), int(qn0), int(qsize), C.c_double(dt), _dp(s.dvv),
+                                        C.c_double(s.consts[0]))
+
     def saxpby(self, a, b, x, y, sweeps=1, nthreads=1) -> float:
         return self.lib.caar_oracle_saxpby(C.c_double(a), C.c_double(b), _dp(x), _dp(y), C.c_size_t(x.size),
                                            sweeps, nthreads)
@@ -185,6 +201,14 @@ class RefOracle:
         assert s.nlev == self.nlev and s.qsize_d == 1 and s.ntl == 3
         return self.lib.caar_ref_run(s.ptr_table(), _ip(s.ctl), C.c_double(s.dt2), _dp(s.consts), _dp(s.dvv),
                                      C.c_double(s.ps0), _dp(s.hyai), ncalls, nthreads)
+
+    def divergence_sphere(self, v, s: State, ie):
+        """The reference's own divergence_sphere on one level of element ie."""
+        out = np.zeros((4, 4))
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        self.lib.caar_ref_divergence_sphere(_dp(v), s.ptr_table(), int(ie), _dp(s.dvv), C.c_double(s.consts[0]),
+                                            _dp(out))
+        return out
 
     def norms(self, s: State, tl=None):
         out = np.zeros(3)

@@ -15,6 +15,7 @@
 
 #include "data_structures.hpp"          // reference header (via -I)
 #include "compute_and_apply_rhs.hpp"    // reference header (via -I)
+#include "sphere_operators.hpp"         // reference header (via -I)
 
 #include <chrono>
 #include <cmath>
@@ -180,6 +181,18 @@ void caar_ref_norms(double* const* arrays, int nets, int nete, int tl, double ou
   out3[0] = std::sqrt(vn);
   out3[1] = std::sqrt(tn);
   out3[2] = std::sqrt(dn);
+}
+
+// The reference's own divergence_sphere (PO/sphere_operators.cpp:50-89) on one 4x4 level `v` [4][4][2] of
+// element `ie` of caller-owned geometry arrays; used to pin the operator the tracer-step oracle is built on.
+void caar_ref_divergence_sphere(const double* v, double* const* arrays, int ie, const double* dvv16, double rrearth,
+                                double* div) {
+  Homme::TestData d;
+  for (int f = 0; f < 16; ++f) *member(d.arrays, f) = arrays[f];
+  d.constants.rrearth = rrearth;
+  for (int i = 0; i < Homme::np; ++i)
+    for (int j = 0; j < Homme::np; ++j) d.deriv.Dvv[i][j] = dvv16[i * Homme::np + j];
+  Homme::divergence_sphere(v, d, ie, div);
 }
 
 }  // extern "C"

@@ -156,3 +156,35 @@ def test_f90_layout_convention_against_fortran_golden(port, golden_dir):
     back = harness.from_f90(harness.to_f90(s.arrays))
     for n in harness.FIELD_NAMES:
         assert np.array_equal(back[n], s.arrays[n]), n
+
+
+def test_divergence_operator_pinned_to_reference(port):
+    """The operator the tracer-step oracle is built on: our restatement of divergence_sphere equals the
+    reference's own function (oracle/_ref) bit for bit on random geometry and fields."""
+    if not harness.ref_available(72):
+        pytest.skip("oracle/_ref not built")
+    ref = harness.RefOracle(72)
+    s = harness.randomize(port.init(5), seed=44)
+    rng = np.random.default_rng(8)
+    for ie in range(5):
+        v = rng.uniform(-30, 30, size=(4, 4, 2))
+        assert np.array_equal(port.divergence_sphere(v, s, ie), ref.divergence_sphere(v, s, ie))
+
+
+def test_euler_step_oracle_properties(port):
+    """Tracer step oracle (LV/EulerStepFunctor.hpp:33-66): dt = 0 returns Qdp(qn0); linear in Qdp; a constant
+    mixing ratio with non-divergent flow... is not testable without DSS, so linearity + the operator pin above."""
+    s = harness.randomize(port.init(4, 24, 3), seed=5)
+    rng = np.random.default_rng(1)
+    vstar = rng.uniform(-20, 20, size=(4, 24, 4, 4, 2))
+    q0 = np.zeros((4, 3, 24, 4, 4))
+    port.euler_step(s, vstar, q0, qn0=1, qsize=3, dt=0.0)
+    assert np.array_equal(q0, s.arrays["elem_state_Qdp"][:, :, 1])
+    qa = np.zeros_like(q0)
+    port.euler_step(s, vstar, qa, qn0=0, qsize=2, dt=300.0)
+    assert np.all(qa[:, 2] == 0.0)                       # tracers >= qsize untouched
+    s2 = s.copy()
+    s2.arrays["elem_state_Qdp"] *= 2.0
+    qb = np.zeros_like(q0)
+    port.euler_step(s2, vstar, qb, qn0=0, qsize=2, dt=300.0)
+    assert np.array_equal(qb, 2.0 * qa)                  # exact: scaling by 2 commutes with every rounding

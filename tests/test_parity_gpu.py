@@ -342,3 +342,31 @@ def test_leapfrog_stepping_with_time_level_rotation(mode):
             assert np.array_equal(got.arrays[n], want.arrays[n]), n
         else:  # rounding differences are amplified by the 5 dependent steps: 1e-12 per step
             assert rel_err(got.arrays[n], want.arrays[n]) <= 5 * TOL, n
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+@pytest.mark.parametrize("nlev,qsize_d,qsize,qn0", [(72, 1, 1, 0), (72, 4, 3, 1), (128, 2, 2, 0), (20, 5, 5, 1)])
+def test_euler_step_tracer_rhs(mode, nlev, qsize_d, qsize, qn0):
+    """qtens = Qdp(qn0) - dt*divergence_sphere(vstar*Qdp(qn0)) against the CPU restatement
+    (operator pinned to the reference's divergence_sphere in tests/test_oracle.py). Strict mode bit-exact."""
+    orc = harness.PortOracle()
+    s = harness.randomize(orc.init(9, nlev, qsize_d), seed=31 + nlev)
+    s.ctl[0:2] = (1, 8)
+    rng = np.random.default_rng(nlev)
+    vstar = rng.uniform(-40.0, 40.0, size=(9, nlev, 4, 4, 2))
+    dt = 150.0
+    want = np.zeros((9, qsize_d, nlev, 4, 4))
+    orc.euler_step(s, vstar, want, qn0, qsize, dt)
+    h = tb.Caar(9, nlev, qsize_d)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.set_control(*[int(x) for x in s.ctl], dt2=s.dt2)
+    h.upload(s.arrays)
+    h.upload_vstar(vstar)
+    h.euler_step(qn0, qsize, dt, mode)
+    got = h.download_qtens()
+    h.close()
+    if mode == tb.MODE_STRICT:
+        assert np.array_equal(got, want)
+    else:
+        assert rel_err(got, want) <= TOL
+    assert np.all(got[0] == 0) and np.all(got[8] == 0) and np.all(got[:, qsize:] == 0)   # outside the ranges: untouched

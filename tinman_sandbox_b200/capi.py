@@ -27,6 +27,7 @@ F_ALL = 0xFFFF
 F_MUTATED = sum(FIELD_BIT[n] for n in MUTATED_FIELDS)
 MODE_FAST, MODE_STRICT = 0, 1
 LAYOUT_CXX, LAYOUT_F90 = 0, 1
+X_VSTAR, X_QTENS = 0, 1
 
 # every symbol include/caar_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -34,7 +35,8 @@ EXPORTED_SYMBOLS = (
     "caar_destroy", "caar_set_params", "caar_set_stream", "caar_upload", "caar_download",
     "caar_device_arrays", "caar_host_register", "caar_host_unregister", "caar_run", "caar_run_host",
     "caar_host_traffic", "caar_upload_layout", "caar_download_layout", "caar_set_params_f90", "caar_run_stepping",
-    "caar_update_time_levels", "caar_sync", "caar_launch_count", "caar_timer_start",
+    "caar_update_time_levels", "caar_extra_count", "caar_extra_upload", "caar_extra_download", "caar_euler_step",
+    "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
     "caar_saxpby_host",
 )
@@ -116,6 +118,11 @@ def load_library():
     lib.caar_run_stepping.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.c_int]
     lib.caar_update_time_levels.argtypes = [C.POINTER(Control)]
     lib.caar_update_time_levels.restype = None
+    lib.caar_extra_count.restype = C.c_size_t
+    lib.caar_extra_count.argtypes = [C.POINTER(Dims), C.c_int]
+    lib.caar_extra_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.caar_extra_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.caar_euler_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
     lib.caar_upload_layout.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int]
     lib.caar_download_layout.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int]
     lib.caar_set_params_f90.argtypes = [C.c_void_p, C.POINTER(Constants), C.POINTER(C.c_double), C.c_double,
@@ -268,6 +275,30 @@ class Caar:
         _check(self.lib, self.lib.caar_run_stepping(self.h, C.byref(self.control), nsteps, mode), "caar_run_stepping")
         if sync:
             self.sync()
+
+    # -- the step after CAAR: tracer advection RHS (LV/EulerStepFunctor.hpp:33-66) ------------------------
+    def upload_vstar(self, vstar):
+        E, L, Q, _ = self.shape_args
+        if vstar.dtype != np.float64 or not vstar.flags["C_CONTIGUOUS"] or vstar.size != E * L * 32:
+            raise CaarError("vstar: need a C-contiguous float64 array [E][L][4][4][2]")
+        _check(self.lib, self.lib.caar_extra_upload(self.h, X_VSTAR, _dp(vstar)), "caar_extra_upload")
+
+    def euler_step(self, qn0, qsize, dt, mode=MODE_FAST, nets=None, nete=None, sync=True):
+        nets = self.control.nets if nets is None else nets
+        nete = self.control.nete if nete is None else nete
+        _check(self.lib, self.lib.caar_euler_step(self.h, nets, nete, int(qn0), int(qsize), float(dt), mode),
+               "caar_euler_step")
+        if sync:
+            self.sync()
+
+    def download_qtens(self, qtens=None):
+        E, L, Q, _ = self.shape_args
+        if qtens is None:
+            qtens = np.zeros((E, Q, L, 4, 4))
+        if qtens.dtype != np.float64 or not qtens.flags["C_CONTIGUOUS"] or qtens.size != E * Q * L * 16:
+            raise CaarError("qtens: need a C-contiguous float64 array [E][qsize_d][L][4][4]")
+        _check(self.lib, self.lib.caar_extra_download(self.h, X_QTENS, _dp(qtens)), "caar_extra_download")
+        return qtens
 
     def compute_and_apply_rhs_host(self, arrays: dict, mode=MODE_FAST, chunk_elems=0):
         """Homme::compute_and_apply_rhs(TestData&) on HOST arrays (PO/main.cpp:113-121 calls it this way):

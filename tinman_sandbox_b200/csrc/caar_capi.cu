@@ -72,6 +72,7 @@ struct caar_handle_s {
   int n_chunk_ev;
   cudaEvent_t ev_fence;
   // caar_run_host zero-copy path: TMA descriptors over the caller's mapped host arrays, rebuilt when they move
+  double* extra[2];  // tracer-step arrays beyond struct Arrays: vstar, qtens (allocated on first use)
   double* stage;  // device staging buffer of the Fortran-layout copies (allocated on first use)
   caar::TmaMaps* tma_host;
   double* tma_host_key[CAAR_NUM_FIELDS];
@@ -213,6 +214,8 @@ int caar_destroy(caar_handle h) {
   if (h->partial) cudaFree(h->partial);
   if (h->out3) cudaFree(h->out3);
   if (h->stage) cudaFree(h->stage);
+  for (int x = 0; x < 2; ++x)
+    if (h->extra[x]) cudaFree(h->extra[x]);
   if (h->out3_host) cudaFreeHost(h->out3_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -570,6 +573,65 @@ int caar_host_traffic(caar_handle h, const caar_control* ctl, int mode, size_t* 
   const size_t n = (size_t)(ctl->nete - ctl->nets);
   *h2d_bytes = in * n * sizeof(double);
   *d2h_bytes = out * n * sizeof(double);
+  return CAAR_OK;
+}
+
+// ---- tracer step after CAAR ---------------------------------------------------------------------------------
+size_t caar_extra_count(const caar_dims* d, int which) {
+  if (!d) return 0;
+  if (which == CAAR_X_VSTAR) return (size_t)d->nelem * d->nlev * 32;
+  if (which == CAAR_X_QTENS) return (size_t)d->nelem * d->qsize_d * d->nlev * 16;
+  return 0;
+}
+
+static int extra_buffer(caar_handle h, int which, double** out) {
+  if (!h) return fail(CAAR_ERR_INVALID, "null handle");
+  if (which != CAAR_X_VSTAR && which != CAAR_X_QTENS) return fail(CAAR_ERR_INVALID, "extra array %d", which);
+  if (!h->extra[which]) {
+    const size_t bytes = caar_extra_count(&h->dims, which) * sizeof(double);
+    CU_TRY(cudaMalloc(&h->extra[which], bytes));
+    CU_TRY(cudaMemsetAsync(h->extra[which], 0, bytes, h->stream));
+  }
+  *out = h->extra[which];
+  return CAAR_OK;
+}
+
+int caar_extra_upload(caar_handle h, int which, const double* host) {
+  if (!host) return fail(CAAR_ERR_INVALID, "null argument");
+  double* dev = nullptr;
+  if (!h) return fail(CAAR_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = extra_buffer(h, which, &dev)) return rc;
+  CU_TRY(cudaMemcpyAsync(dev, host, caar_extra_count(&h->dims, which) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return CAAR_OK;
+}
+
+int caar_extra_download(caar_handle h, int which, double* host) {
+  if (!host) return fail(CAAR_ERR_INVALID, "null argument");
+  double* dev = nullptr;
+  if (!h) return fail(CAAR_ERR_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = extra_buffer(h, which, &dev)) return rc;
+  CU_TRY(cudaMemcpyAsync(host, dev, caar_extra_count(&h->dims, which) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return CAAR_OK;
+}
+
+int caar_euler_step(caar_handle h, int nets, int nete, int qn0, int qsize, double dt, int mode) {
+  if (!h) return fail(CAAR_ERR_INVALID, "null handle");
+  if (!h->params_set) return fail(CAAR_ERR_STATE, "caar_set_params must be called before caar_euler_step");
+  if (nets < 0 || nete > h->dims.nelem || nets > nete) return fail(CAAR_ERR_INVALID, "element range [%d,%d)", nets, nete);
+  if (qn0 < 0 || qn0 > 1) return fail(CAAR_ERR_INVALID, "qn0=%d must be 0 or 1", qn0);
+  if (qsize < 0 || qsize > h->dims.qsize_d) return fail(CAAR_ERR_INVALID, "qsize=%d outside [0,%d]", qsize, h->dims.qsize_d);
+  if (mode != CAAR_MODE_FAST && mode != CAAR_MODE_STRICT) return fail(CAAR_ERR_INVALID, "mode=%d", mode);
+  DeviceGuard guard(h->device);
+  double *vstar = nullptr, *qtens = nullptr;
+  if (int rc = extra_buffer(h, CAAR_X_VSTAR, &vstar)) return rc;
+  if (int rc = extra_buffer(h, CAAR_X_QTENS, &qtens)) return rc;
+  const caar::KernelArgs a = make_args(h, nullptr);
+  CU_TRY(caar::launch_euler_step(a, vstar, qtens, nets, nete, qn0, qsize, dt, mode == CAAR_MODE_STRICT, h->stream));
+  if (nete > nets && qsize > 0) ++h->launches;
   return CAAR_OK;
 }
 

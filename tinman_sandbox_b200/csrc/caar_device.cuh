@@ -70,6 +70,9 @@ cudaError_t launch_norms(const KernelArgs& a, int tl, int nets, int nete, double
 cudaError_t launch_relayout(double* cxx, double* f90, size_t nblocks, int kind, bool to_cxx, int q_dim, int nlev,
                             size_t blk0, cudaStream_t s);
 cudaError_t launch_reciprocal(double* out, const double* in, size_t n, cudaStream_t s);
+// tracer step after CAAR (caar_euler.cu): qtens = Qdp(qn0) - dt*divergence_sphere(vstar*Qdp(qn0))
+cudaError_t launch_euler_step(const KernelArgs& a, const double* vstar, double* qtens, int nets, int nete, int qn0,
+                              int qsize, double dt, bool strict, cudaStream_t s);
 cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t n, cudaStream_t s);
 
 }  // namespace caar
