@@ -155,6 +155,16 @@ int caar_destroy(caar_handle h);
 int caar_set_params(caar_handle h, const caar_constants* c, const double dvv[16], double ps0,
                     const double* hyai);
 
+/* Vertical coordinate of the following caar_run* calls. rsplit > 0 (default 1): vertically
+   Lagrangian — eta_dot_dpdn = T_vadv = v_vadv = 0, the only branch the reference's C++ code runs
+   (PO/compute_and_apply_rhs.cpp:164-171,222-231). rsplit == 0: Eulerian — eta_dot_dpdn at the interfaces from the
+   running sum of div(v dp) and hybi, vertical advection of T and v (preq_vertadv), the dp3d update with the
+   vertical flux difference, and derived_eta_dot_dpdn accumulates the real flux:
+   F/routine_extracted.F90:227-262,270-277,325-334,515-517; LV/CaarFunctor.hpp:504-547. hybi has nlev+1 entries
+   (F hvcoord%hybi; ignored when rsplit > 0). The reference holds no runnable implementation of this branch:
+   parity is against the tests' own CPU restatement of these formulas only ("parity unpinned"). */
+int caar_set_vertical_coordinate(caar_handle h, int rsplit, const double* hybi);
+
 /* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all later work; NULL restores the
    handle's own stream. Lets a torch program time the kernels with its own events. */
 int caar_set_stream(caar_handle h, void* cuda_stream);

@@ -48,6 +48,10 @@ typedef struct {
   const double* dvv;         /* [4][4] row-major */
   double ps0;
   const double* hyai;
+  /* vertical coordinate: rsplit > 0 = vertically Lagrangian (the only branch the C++ reference runs),
+   * rsplit == 0 = Eulerian (fortran/routine_extracted.F90:227-262), which needs hybi[nlev+1] */
+  int rsplit;
+  const double* hybi;
 } ctx_t;
 
 size_t caar_oracle_field_count(int f, int E, int L, int Q, int ntl) {
@@ -181,16 +185,18 @@ static void omega_ps(int L, const double* p, const double* vgrad_p, const double
 
 typedef struct {
   double *p, *grad_p, *vgrad_p, *vdp, *divdp, *vort, *T_v, *omega, *phii, *vt1, *vt2, *tt;
+  double* eta; /* [L+1][16] interface values of eta_dot_dpdn (Eulerian branch) */
 } scratch_t;
 
 static int scratch_alloc(scratch_t* w, int L) {
   const size_t n = (size_t)L * PTS;
-  double* base = (double*)calloc(n * 14, sizeof(double));
+  double* base = (double*)calloc(n * 14 + n + PTS, sizeof(double));
   if (!base) return -1;
   w->p = base;            w->grad_p = base + n;      w->vgrad_p = base + 3 * n;
   w->vdp = base + 4 * n;  w->divdp = base + 6 * n;   w->vort = base + 7 * n;
   w->T_v = base + 8 * n;  w->omega = base + 9 * n;   w->phii = base + 10 * n;
   w->vt1 = base + 11 * n; w->vt2 = base + 12 * n;    w->tt = base + 13 * n;
+  w->eta = base + 14 * n;
   return 0;
 }
 
@@ -251,8 +257,33 @@ static void rhs_element(const ctx_t* c, int ie, scratch_t* w) {
   hydrostatic(L, phis, w->T_v, w->p, dp_n0, c->Rgas, w->phii, phi);
   omega_ps(L, w->p, w->vgrad_p, w->divdp, w->omega);
 
-  /* F: accumulate the derived fields (PO:164-183). eta_dot_dpdn_tmp is identically zero. */
-  {
+  /* Eulerian branch (rsplit == 0), which the C++ reference leaves out ("-0" placeholders, PO:222-231) and the
+   * Fortran reference specifies: eta_dot_dpdn at the L+1 interfaces from the running sum of divdp and hybi,
+   * fortran/routine_extracted.F90:233-254. NOT pinned by any runnable reference (no Fortran compiler, no known
+   * answers): "parity unpinned" for this branch. */
+  if (c->rsplit == 0) {
+    double sdot[PTS];
+    for (int q = 0; q < PTS; ++q) sdot[q] = 0.0;
+    for (int k = 0; k < L; ++k)
+      for (int q = 0; q < PTS; ++q) {
+        sdot[q] += w->divdp[k * PTS + q];
+        w->eta[(k + 1) * PTS + q] = sdot[q];
+      }
+    for (int k = 0; k < L - 1; ++k)
+      for (int q = 0; q < PTS; ++q)
+        w->eta[(k + 1) * PTS + q] = c->hybi[k + 1] * sdot[q] - w->eta[(k + 1) * PTS + q];
+    for (int q = 0; q < PTS; ++q) {
+      w->eta[q] = 0.0;
+      w->eta[(size_t)L * PTS + q] = 0.0;
+    }
+  }
+
+  /* F: accumulate the derived fields (PO:164-183). eta_dot_dpdn_tmp is identically zero on the Lagrangian
+   * branch; fortran/routine_extracted.F90:270-277 on the Eulerian one. */
+  if (c->rsplit == 0) {
+    for (size_t n = 0; n < lf + PTS; ++n) eta_dot[n] += c->eta_ave_w * w->eta[n];
+    for (size_t n = 0; n < lf; ++n) omega_p[n] += c->eta_ave_w * w->omega[n];
+  } else {
     const double zero = 0.0;
     for (size_t n = 0; n < lf; ++n) {
       eta_dot[n] += c->eta_ave_w * zero;
@@ -275,6 +306,40 @@ static void rhs_element(const ctx_t* c, int ie, scratch_t* w) {
     }
     grad_sphere(Ephi, c->dvv, Dinv, c->rrearth, gE);
     const double* gp = w->grad_p + (size_t)k * PTS * 2;
+    if (c->rsplit == 0) {
+      /* preq_vertadv, CCM2 (3.b.1): level_vectorized_ppscan/CaarFunctor.hpp:504-547 (rpdel = 1/dp,
+       * fortran/routine_extracted.F90:120), then the tendencies with the Fortran signs
+       * (fortran/routine_extracted.F90:325-334: ttens = -T_vadv - vgrad_T + kappa*T_v*omega_p) */
+      for (int q = 0; q < PTS; ++q) {
+        const size_t n = (size_t)k * PTS + q;
+        const double rdp = 1.0 / dp_n0[n];
+        const double facp = 0.5 * rdp * w->eta[(k + 1) * PTS + q];
+        const double facm = 0.5 * rdp * w->eta[k * PTS + q];
+        double T_vadv, v_vadv0, v_vadv1;
+        if (k == 0) {
+          T_vadv = facp * (T_n0[n + PTS] - T_n0[n]);
+          v_vadv0 = facp * (v_n0[(n + PTS) * 2] - v_n0[n * 2]);
+          v_vadv1 = facp * (v_n0[(n + PTS) * 2 + 1] - v_n0[n * 2 + 1]);
+        } else if (k < L - 1) {
+          T_vadv = facp * (T_n0[n + PTS] - T_n0[n]) + facm * (T_n0[n] - T_n0[n - PTS]);
+          v_vadv0 = facp * (v_n0[(n + PTS) * 2] - v_n0[n * 2]) + facm * (v_n0[n * 2] - v_n0[(n - PTS) * 2]);
+          v_vadv1 = facp * (v_n0[(n + PTS) * 2 + 1] - v_n0[n * 2 + 1]) +
+                    facm * (v_n0[n * 2 + 1] - v_n0[(n - PTS) * 2 + 1]);
+        } else {
+          T_vadv = facm * (T_n0[n] - T_n0[n - PTS]);
+          v_vadv0 = facm * (v_n0[n * 2] - v_n0[(n - PTS) * 2]);
+          v_vadv1 = facm * (v_n0[n * 2 + 1] - v_n0[(n - PTS) * 2 + 1]);
+        }
+        const double gpterm = w->T_v[n] / w->p[n];
+        const double glnps1 = c->Rgas * gpterm * gp[q * 2];
+        const double glnps2 = c->Rgas * gpterm * gp[q * 2 + 1];
+        const double v1 = v_n0[n * 2], v2 = v_n0[n * 2 + 1];
+        w->vt1[n] = -v_vadv0 + v2 * (fcor[q] + w->vort[n]) - gE[q * 2] - glnps1;
+        w->vt2[n] = -v_vadv1 - v1 * (fcor[q] + w->vort[n]) - gE[q * 2 + 1] - glnps2;
+        w->tt[n] = -T_vadv - vgrad_T[q] + c->kappa * w->T_v[n] * w->omega[n];
+      }
+      continue;
+    }
     for (int q = 0; q < PTS; ++q) {
       const double v_vadv0 = 0.0, v_vadv1 = 0.0, T_vadv = 0.0;
       const double gpterm = w->T_v[k * PTS + q] / w->p[k * PTS + q];
@@ -301,7 +366,10 @@ static void rhs_element(const ctx_t* c, int ie, scratch_t* w) {
         v_np1[n * 2] = spheremp[q] * (v_nm1[n * 2] + c->dt2 * w->vt1[n]);
         v_np1[n * 2 + 1] = spheremp[q] * (v_nm1[n * 2 + 1] + c->dt2 * w->vt2[n]);
         T_np1[n] = spheremp[q] * (T_nm1[n] + c->dt2 * w->tt[n]);
-        dp_np1[n] = spheremp[q] * (dp_nm1[n] - c->dt2 * w->divdp[n]);
+        if (c->rsplit == 0) /* fortran/routine_extracted.F90:515-517 */
+          dp_np1[n] = spheremp[q] * (dp_nm1[n] - c->dt2 * (w->divdp[n] + w->eta[n + PTS] - w->eta[n]));
+        else
+          dp_np1[n] = spheremp[q] * (dp_nm1[n] - c->dt2 * w->divdp[n]);
       }
   }
 }
@@ -329,11 +397,29 @@ static double now_s(void) {
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+static double run_impl(int nlev, int qsize_d, int ntl, double* const* arrays, const int* ctl, double dt2,
+                       const double* k6, const double* dvv16, double ps0, const double* hyai, int rsplit,
+                       const double* hybi, int ncalls, int nthreads);
+
 double caar_oracle_run(int nlev, int qsize_d, int ntl, double* const* arrays, const int* ctl, double dt2,
                        const double* k6, const double* dvv16, double ps0, const double* hyai, int ncalls,
                        int nthreads) {
+  return run_impl(nlev, qsize_d, ntl, arrays, ctl, dt2, k6, dvv16, ps0, hyai, 1, NULL, ncalls, nthreads);
+}
+
+/* the Eulerian (rsplit == 0) branch: fortran/routine_extracted.F90:227-262,325-334,515-517 */
+double caar_oracle_run_eulerian(int nlev, int qsize_d, int ntl, double* const* arrays, const int* ctl, double dt2,
+                                const double* k6, const double* dvv16, double ps0, const double* hyai,
+                                const double* hybi, int ncalls, int nthreads) {
+  return run_impl(nlev, qsize_d, ntl, arrays, ctl, dt2, k6, dvv16, ps0, hyai, 0, hybi, ncalls, nthreads);
+}
+
+static double run_impl(int nlev, int qsize_d, int ntl, double* const* arrays, const int* ctl, double dt2,
+                       const double* k6, const double* dvv16, double ps0, const double* hyai, int rsplit,
+                       const double* hybi, int ncalls, int nthreads) {
   ctx_t c;
   memset(&c, 0, sizeof c);
+  c.rsplit = rsplit; c.hybi = hybi;
   c.nlev = nlev; c.qsize_d = qsize_d; c.ntl = ntl; c.a = arrays;
   c.nets = ctl[0]; c.nete = ctl[1]; c.n0 = ctl[2]; c.np1 = ctl[3]; c.nm1 = ctl[4]; c.qn0 = ctl[5];
   c.dt2 = dt2;

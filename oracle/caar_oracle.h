@@ -21,6 +21,14 @@ double caar_oracle_run(int nlev, int qsize_d, int ntl, double* const* arrays, co
                        const double* consts6, const double* dvv16, double ps0, const double* hyai,
                        int ncalls, int nthreads);
 
+/* the same with the Eulerian vertical coordinate (rsplit == 0: eta_dot_dpdn from the divergence sum and hybi,
+ * vertical advection of T and v; fortran/routine_extracted.F90:227-262,325-334,515-517 and preq_vertadv,
+ * level_vectorized_ppscan/CaarFunctor.hpp:504-547). hybi has nlev+1 entries. PARITY UNPINNED: the C++ reference
+ * does not implement this branch and the Fortran one cannot be compiled here. */
+double caar_oracle_run_eulerian(int nlev, int qsize_d, int ntl, double* const* arrays, const int* ctl6i, double dt2,
+                                const double* consts6, const double* dvv16, double ps0, const double* hyai,
+                                const double* hybi, int ncalls, int nthreads);
+
 /* the three printed norms (PO/compute_and_apply_rhs.cpp:354-399) of time level tl */
 void caar_oracle_norms(int nlev, int ntl, double* const* arrays, int nets, int nete, int tl,
                        double out3[3]);

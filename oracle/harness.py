@@ -133,6 +133,7 @@ class PortOracle:
         self.lib = C.CDLL(build_port())
         L = self.lib
         L.caar_oracle_run.restype = C.c_double
+        L.caar_oracle_run_eulerian.restype = C.c_double
         L.caar_oracle_saxpby.restype = C.c_double
         L.caar_oracle_field_count.restype = C.c_size_t
 
@@ -148,6 +149,14 @@ class PortOracle:
         return self.lib.caar_oracle_run(s.nlev, s.qsize_d, s.ntl, s.ptr_table(), _ip(s.ctl),
                                         C.c_double(s.dt2), _dp(s.consts), _dp(s.dvv), C.c_double(s.ps0),
                                         _dp(s.hyai), ncalls, nthreads)
+
+    def run_eulerian(self, s: State, hybi, ncalls=1, nthreads=1) -> float:
+        """rsplit == 0 branch (fortran/routine_extracted.F90:227-262); PARITY UNPINNED restatement."""
+        hybi = np.ascontiguousarray(hybi, dtype=np.float64)
+        assert hybi.size == s.nlev + 1
+        return self.lib.caar_oracle_run_eulerian(s.nlev, s.qsize_d, s.ntl, s.ptr_table(), _ip(s.ctl),
+                                                 C.c_double(s.dt2), _dp(s.consts), _dp(s.dvv), C.c_double(s.ps0),
+                                                 _dp(s.hyai), _dp(hybi), ncalls, nthreads)
 
     def norms(self, s: State, tl=None):
         out = np.zeros(3)

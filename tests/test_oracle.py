@@ -188,3 +188,36 @@ def test_euler_step_oracle_properties(port):
     qb = np.zeros_like(q0)
     port.euler_step(s2, vstar, qb, qn0=0, qsize=2, dt=300.0)
     assert np.array_equal(qb, 2.0 * qa)                  # exact: scaling by 2 commutes with every rounding
+
+
+def test_eulerian_branch_oracle_properties(port):
+    """rsplit == 0 restatement (fortran/routine_extracted.F90:227-262; PARITY UNPINNED): the properties the
+    Fortran formulas imply. (1) the vertical flux telescopes (eta = 0 at top and bottom), so the column sum of
+    dp3d(np1)/spheremp equals the Lagrangian branch's; (2) with vertically uniform T and v the vertical
+    advection vanishes and T, v come out as on the Lagrangian branch; (3) hybi only enters through eta."""
+    L = 24
+    base = harness.randomize(port.init(3, L), seed=17)
+    hybi = np.linspace(0.0, 1.0, L + 1) ** 2
+    lag, eul = base.copy(), base.copy()
+    port.run(lag)
+    port.run_eulerian(eul, hybi)
+    mp = base.arrays["elem_spheremp"][:, None]
+    col_l = (lag.arrays["elem_state_dp3d"][:, 1] / mp).sum(axis=1)
+    col_e = (eul.arrays["elem_state_dp3d"][:, 1] / mp).sum(axis=1)
+    assert np.max(np.abs(col_l - col_e) / np.abs(col_l)) < 1e-12
+    assert not np.array_equal(lag.arrays["elem_state_dp3d"], eul.arrays["elem_state_dp3d"])
+    assert not np.array_equal(lag.arrays["elem_state_T"], eul.arrays["elem_state_T"])
+    for n in ("elem_derived_phi", "elem_derived_omega_p", "elem_derived_vn0"):       # no vertical-flux term in these
+        assert np.array_equal(lag.arrays[n], eul.arrays[n]), n
+    # interfaces 0 and L carry no flux
+    d_eta = eul.arrays["elem_derived_eta_dot_dpdn"] - base.arrays["elem_derived_eta_dot_dpdn"]
+    assert np.all(d_eta[:, 0] == 0) and np.all(d_eta[:, L] == 0) and np.any(d_eta[:, 1:L] != 0)
+    # vertically uniform T and v: no vertical advection
+    uni = base.copy()
+    uni.arrays["elem_state_T"][:, :, :] = uni.arrays["elem_state_T"][:, :, :1]
+    uni.arrays["elem_state_v"][:, :, :] = uni.arrays["elem_state_v"][:, :, :1]
+    lag2, eul2 = uni.copy(), uni.copy()
+    port.run(lag2)
+    port.run_eulerian(eul2, hybi)
+    assert np.array_equal(lag2.arrays["elem_state_T"], eul2.arrays["elem_state_T"])
+    assert np.array_equal(lag2.arrays["elem_state_v"], eul2.arrays["elem_state_v"])

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "caar_last_error", "caar_version", "caar_field_count", "caar_device_count", "caar_create",
     "caar_destroy", "caar_set_params", "caar_set_stream", "caar_upload", "caar_download",
     "caar_device_arrays", "caar_host_register", "caar_host_unregister", "caar_run", "caar_run_host",
-    "caar_host_traffic", "caar_upload_layout", "caar_download_layout", "caar_set_params_f90", "caar_run_stepping",
+    "caar_host_traffic", "caar_upload_layout", "caar_download_layout", "caar_set_params_f90", "caar_set_vertical_coordinate", "caar_run_stepping",
     "caar_update_time_levels", "caar_extra_count", "caar_extra_upload", "caar_extra_download", "caar_euler_step",
     "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
@@ -115,6 +115,7 @@ def load_library():
     lib.caar_run_host.argtypes = [C.c_void_p, C.POINTER(Arrays), C.POINTER(Control), C.c_int, C.c_int]
     lib.caar_host_traffic.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.POINTER(C.c_size_t),
                                       C.POINTER(C.c_size_t)]
+    lib.caar_set_vertical_coordinate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     lib.caar_run_stepping.argtypes = [C.c_void_p, C.POINTER(Control), C.c_int, C.c_int]
     lib.caar_update_time_levels.argtypes = [C.POINTER(Control)]
     lib.caar_update_time_levels.restype = None
@@ -205,6 +206,16 @@ class Caar:
             raise CaarError("hyai needs nlev+1 entries")
         _check(self.lib, self.lib.caar_set_params(self.h, C.byref(c), _dp(dvv), float(ps0), _dp(hyai)),
                "caar_set_params")
+
+    def set_vertical_coordinate(self, rsplit, hybi=None):
+        """rsplit > 0: vertically Lagrangian (default); rsplit == 0: Eulerian, needs hybi (nlev+1,)
+        (F/routine_extracted.F90:227-262)."""
+        if hybi is not None:
+            hybi = np.ascontiguousarray(hybi, dtype=np.float64)
+            if hybi.size != self.dims.nlev + 1:
+                raise CaarError("hybi needs nlev+1 entries")
+        _check(self.lib, self.lib.caar_set_vertical_coordinate(self.h, int(rsplit), _dp(hybi) if hybi is not None else None),
+               "caar_set_vertical_coordinate")
 
     def set_control(self, nets=None, nete=None, n0=None, np1=None, nm1=None, qn0=None, dt2=None):
         c = self.control

@@ -72,6 +72,8 @@ struct caar_handle_s {
   int n_chunk_ev;
   cudaEvent_t ev_fence;
   // caar_run_host zero-copy path: TMA descriptors over the caller's mapped host arrays, rebuilt when they move
+  int rsplit;        // > 0 vertically Lagrangian (default 1), 0 Eulerian
+  double* hybi_dev;  // [nlev+1], Eulerian branch only
   double* extra[2];  // tracer-step arrays beyond struct Arrays: vstar, qtens (allocated on first use)
   double* stage;  // device staging buffer of the Fortran-layout copies (allocated on first use)
   caar::TmaMaps* tma_host;
@@ -106,6 +108,16 @@ int validate_control(const caar_handle_s* h, const caar_control* ctl) {
   return CAAR_OK;
 }
 
+// the fused kernels cover the vertically Lagrangian branch, and the Eulerian one where launch_fused says so;
+// everything else runs on the generic reference-order kernel (still on the GPU)
+bool uses_fused(const caar_handle_s* h, int mode) {
+  return mode == CAAR_MODE_FAST && caar::fused_supports(h->dims.nlev) &&
+         (h->rsplit > 0 || caar::fused_supports_eulerian(h->dims.nlev));
+}
+// eta_dot_dpdn travels when the kernel really updates it: the reference-order kernel always does (+= 0 included),
+// the fused kernels only on the Eulerian branch
+bool moves_eta(const caar_handle_s* h, int mode) { return !uses_fused(h, mode) || h->rsplit == 0; }
+
 caar::KernelArgs make_args(const caar_handle_s* h, const caar_control* ctl, double* const* ptr = nullptr) {
   caar::KernelArgs a;
   std::memset(&a, 0, sizeof a);
@@ -123,6 +135,8 @@ caar::KernelArgs make_args(const caar_handle_s* h, const caar_control* ctl, doub
   a.kappa = h->c.kappa; a.hyai0 = h->hyai0; a.ps0 = h->ps0;
   for (int i = 0; i < 16; ++i) a.dvv[i] = h->dvv[i];
   a.tma = h->tma;
+  a.rsplit = h->rsplit;
+  a.hybi = h->hybi_dev;
   return a;
 }
 
@@ -193,6 +207,7 @@ int caar_create(caar_handle* out, const caar_dims* dims, int device) {
     return code;
   }
   h->stream = h->own_stream;
+  h->rsplit = 1;
   if (dims->nlev == 72 || dims->nlev == 128) {
     h->tma = new (std::nothrow) caar::TmaMaps();
     char msg[256] = "host allocation failed";
@@ -216,6 +231,7 @@ int caar_destroy(caar_handle h) {
   if (h->stage) cudaFree(h->stage);
   for (int x = 0; x < 2; ++x)
     if (h->extra[x]) cudaFree(h->extra[x]);
+  if (h->hybi_dev) cudaFree(h->hybi_dev);
   if (h->out3_host) cudaFreeHost(h->out3_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -238,6 +254,21 @@ int caar_set_params(caar_handle h, const caar_constants* c, const double dvv[16]
   h->ps0 = ps0;
   h->hyai0 = hyai[0];
   h->params_set = true;
+  return CAAR_OK;
+}
+
+int caar_set_vertical_coordinate(caar_handle h, int rsplit, const double* hybi) {
+  if (!h) return fail(CAAR_ERR_INVALID, "null handle");
+  if (rsplit < 0) return fail(CAAR_ERR_INVALID, "rsplit=%d", rsplit);
+  if (rsplit == 0) {
+    if (!hybi) return fail(CAAR_ERR_INVALID, "rsplit=0 (Eulerian) needs hybi[nlev+1]");
+    DeviceGuard guard(h->device);
+    const size_t bytes = (size_t)(h->dims.nlev + 1) * sizeof(double);
+    if (!h->hybi_dev) CU_TRY(cudaMalloc(&h->hybi_dev, bytes));
+    CU_TRY(cudaMemcpyAsync(h->hybi_dev, hybi, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+  }
+  h->rsplit = rsplit;
   return CAAR_OK;
 }
 
@@ -365,7 +396,7 @@ int caar_run(caar_handle h, const caar_control* ctl, int nsteps, int mode) {
   if (mode != CAAR_MODE_FAST && mode != CAAR_MODE_STRICT) return fail(CAAR_ERR_INVALID, "mode=%d", mode);
   DeviceGuard guard(h->device);
   const caar::KernelArgs a = make_args(h, ctl);
-  const bool fast = (mode == CAAR_MODE_FAST) && caar::fused_supports(h->dims.nlev);
+  const bool fast = uses_fused(h, mode);
   if (!fast && caar::strict_smem_bytes(h->dims.nlev) > 200 * 1024)
     return fail(CAAR_ERR_UNSUPPORTED, "nlev=%d too large for the strict kernel", h->dims.nlev);
   if (ctl->nete == ctl->nets) return CAAR_OK;
@@ -453,7 +484,7 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
   if (mode != CAAR_MODE_FAST && mode != CAAR_MODE_STRICT) return fail(CAAR_ERR_INVALID, "mode=%d", mode);
   if (chunk_elems < 0 && chunk_elems != CAAR_HOST_ZERO_COPY) return fail(CAAR_ERR_INVALID, "chunk_elems=%d", chunk_elems);
   const caar_dims& d = h->dims;
-  const bool fast = (mode == CAAR_MODE_FAST) && caar::fused_supports(d.nlev);
+  const bool fast = uses_fused(h, mode);
   if (!fast && caar::strict_smem_bytes(d.nlev) > 200 * 1024)
     return fail(CAAR_ERR_UNSUPPORTED, "nlev=%d too large for the strict kernel", d.nlev);
   const int n = ctl->nete - ctl->nets;
@@ -477,7 +508,7 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
   out[no++] = Slice{12, lf, 0, lf};
   out[no++] = Slice{13, lf, 0, lf};
   out[no++] = Slice{15, 2 * lf, 0, 2 * lf};
-  if (!fast) {  // the reference-order kernel also performs eta_dot_dpdn += eta_ave_w*0 (PO:164-171)
+  if (moves_eta(h, mode)) {  // reference-order kernel: eta_dot_dpdn += eta_ave_w*0 (PO:164-171); Eulerian: the real flux
     const size_t le = (size_t)(d.nlev + 1) * 16;
     in[ni++] = Slice{11, le, 0, le};
     out[no++] = Slice{11, le, 0, le};
@@ -565,11 +596,13 @@ int caar_host_traffic(caar_handle h, const caar_control* ctl, int mode, size_t* 
   if (!h || !ctl || !h2d_bytes || !d2h_bytes) return fail(CAAR_ERR_INVALID, "null argument");
   if (int rc = validate_control(h, ctl)) return rc;
   const caar_dims& d = h->dims;
-  const bool fast = (mode == CAAR_MODE_FAST) && caar::fused_supports(d.nlev);
+  const bool fast = uses_fused(h, mode);
   const size_t lf = (size_t)d.nlev * 16, le = (size_t)(d.nlev + 1) * 16;
   const size_t lv = (ctl->n0 == ctl->nm1) ? 1 : 2;
-  size_t in = 2 * 64 + 5 * 16 + lv * 4 * lf + (ctl->qn0 != -1 ? lf : 0) + 4 * lf + (fast ? 0 : le);
-  size_t out = 8 * lf + (fast ? 0 : le);
+  (void)fast;
+  const size_t eta = moves_eta(h, mode) ? le : 0;
+  size_t in = 2 * 64 + 5 * 16 + lv * 4 * lf + (ctl->qn0 != -1 ? lf : 0) + 4 * lf + eta;
+  size_t out = 8 * lf + eta;
   const size_t n = (size_t)(ctl->nete - ctl->nets);
   *h2d_bytes = in * n * sizeof(double);
   *d2h_bytes = out * n * sizeof(double);

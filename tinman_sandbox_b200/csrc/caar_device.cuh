@@ -44,6 +44,10 @@ struct KernelArgs {
   double dvv[16];
   // host pointer to the handle's TMA descriptors (TmaMaps), or null; only the launcher reads it
   const void* tma;
+  // vertical coordinate: rsplit > 0 vertically Lagrangian (the reference's C++ path), rsplit == 0 Eulerian
+  // (F/routine_extracted.F90:227-262) with hybi[nlev+1] in device memory
+  int rsplit;
+  const double* hybi;
   // L2 prefetch distance in elements (0 = off): CTA e prefetches the early inputs of element e + pf_dist
   int pf_dist;
 };
@@ -60,6 +64,7 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen);
 cudaError_t launch_strict(const KernelArgs& a, cudaStream_t s);
 cudaError_t launch_fused(const KernelArgs& a, cudaStream_t s);
 bool fused_supports(int nlev);
+bool fused_supports_eulerian(int nlev);  // rsplit == 0 on the fused path
 cudaError_t launch_fused_ldg(const KernelArgs& a, cudaStream_t s);
 bool fused_ldg_supports(int nlev);
 size_t strict_smem_bytes(int nlev);

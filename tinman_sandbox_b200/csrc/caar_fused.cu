@@ -704,6 +704,8 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   return 0;
 }
 
+bool fused_supports_eulerian(int) { return false; }
+
 bool fused_supports(int nlev) { return nlev == 72 || nlev == 128 || fused_ldg_supports(nlev); }
 
 cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {

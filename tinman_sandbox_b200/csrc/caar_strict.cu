@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(512) caar_strict_kernel(const KernelArgs A) {
   double* Tv = vort + lf;         // [L][16]
   double* om = Tv + lf;           // [L][16]
   double* ph = om + lf;           // [L][16]      phii during the scan, then Ephi
+  double* eta = ph + lf;          // [L+1][16]    eta_dot_dpdn at the interfaces (Eulerian branch only)
+  const bool eul = (A.rsplit == 0);
   __shared__ double geo_D[64], geo_Dinv[64], geo_met[16], geo_rmet[16], s_dvv[16];
 
   const int ie = A.nets + blockIdx.x;
@@ -179,12 +181,24 @@ __global__ void __launch_bounds__(512) caar_strict_kernel(const KernelArgs A) {
     const double ckl = mul(2.0, ckk);
     term = divdp[k * PTS + q];
     om[k * PTS + q] = sub(sub(dvd(vgp[k * PTS + q], p[k * PTS + q]), mul(ckl, suml)), mul(ckk, term));
+  } else if (eul && tid >= 64 && tid < 64 + PTS) {
+    // Eulerian branch: eta_dot_dpdn at the interfaces from the running sum of divdp and hybi
+    // (F/routine_extracted.F90:233-254), on warp 2
+    const int q = tid - 64;
+    double sdot = 0.0;
+    for (int k = 0; k < L; ++k) {
+      sdot = add(sdot, divdp[k * PTS + q]);
+      eta[(k + 1) * PTS + q] = sdot;
+    }
+    for (int k = 0; k < L - 1; ++k) eta[(k + 1) * PTS + q] = sub(mul(A.hybi[k + 1], sdot), eta[(k + 1) * PTS + q]);
+    eta[q] = 0.0;
+    eta[L * PTS + q] = 0.0;
   }
   __syncthreads();
 
-  // F: accumulate derived fields (PO:164-183); Ephi (PO:196)
+  // F: accumulate derived fields (PO:164-183; Eulerian: F/routine_extracted.F90:270-277); Ephi (PO:196)
   for (int n = tid; n < lf + PTS; n += nt) {
-    eta_dot[n] = add(eta_dot[n], mul(A.eta_ave_w, 0.0));
+    eta_dot[n] = add(eta_dot[n], mul(A.eta_ave_w, eul ? eta[n] : 0.0));
     if (n < lf) {
       omega_p[n] = add(omega_p[n], mul(A.eta_ave_w, om[n]));
       const double v1 = v_n0[n * 2], v2 = v_n0[n * 2 + 1];
@@ -205,11 +219,35 @@ __global__ void __launch_bounds__(512) caar_strict_kernel(const KernelArgs A) {
     const double glnps1 = mul(mul(A.Rgas, gpterm), gp[n * 2]);
     const double glnps2 = mul(mul(A.Rgas, gpterm), gp[n * 2 + 1]);
     const double fv = add(fcor[q], vort[n]);
-    // -v_vadv + ... with v_vadv == +0.0: (-0.0) + x == x and (-0.0) - x == -x for every x
-    const double vt1 = sub(sub(mul(v2, fv), e0), glnps1);
-    const double vt2 = sub(sub(-mul(v1, fv), e1), glnps2);
-    // T_vadv - vgrad_T with T_vadv == +0.0
-    const double tt = add(sub(0.0, vgrad_T), mul(mul(A.kappa, Tv[n]), om[n]));
+    double vt1, vt2, tt;
+    if (eul) {
+      // preq_vertadv (LV/CaarFunctor.hpp:504-547) and the Fortran tendencies (F/routine_extracted.F90:325-334)
+      const double rdp = dvd(1.0, dp_n0[n]);
+      const double facp = mul(mul(0.5, rdp), eta[n + PTS]), facm = mul(mul(0.5, rdp), eta[n]);
+      double T_vadv, vv0, vv1;
+      if (k == 0) {
+        T_vadv = mul(facp, sub(T_n0[n + PTS], T_n0[n]));
+        vv0 = mul(facp, sub(v_n0[(n + PTS) * 2], v1));
+        vv1 = mul(facp, sub(v_n0[(n + PTS) * 2 + 1], v2));
+      } else if (k < L - 1) {
+        T_vadv = add(mul(facp, sub(T_n0[n + PTS], T_n0[n])), mul(facm, sub(T_n0[n], T_n0[n - PTS])));
+        vv0 = add(mul(facp, sub(v_n0[(n + PTS) * 2], v1)), mul(facm, sub(v1, v_n0[(n - PTS) * 2])));
+        vv1 = add(mul(facp, sub(v_n0[(n + PTS) * 2 + 1], v2)), mul(facm, sub(v2, v_n0[(n - PTS) * 2 + 1])));
+      } else {
+        T_vadv = mul(facm, sub(T_n0[n], T_n0[n - PTS]));
+        vv0 = mul(facm, sub(v1, v_n0[(n - PTS) * 2]));
+        vv1 = mul(facm, sub(v2, v_n0[(n - PTS) * 2 + 1]));
+      }
+      vt1 = sub(sub(add(-vv0, mul(v2, fv)), e0), glnps1);
+      vt2 = sub(sub(sub(-vv1, mul(v1, fv)), e1), glnps2);
+      tt = add(sub(-T_vadv, vgrad_T), mul(mul(A.kappa, Tv[n]), om[n]));
+    } else {
+      // -v_vadv + ... with v_vadv == +0.0: (-0.0) + x == x and (-0.0) - x == -x for every x
+      vt1 = sub(sub(mul(v2, fv), e0), glnps1);
+      vt2 = sub(sub(-mul(v1, fv), e1), glnps2);
+      // T_vadv - vgrad_T with T_vadv == +0.0
+      tt = add(sub(0.0, vgrad_T), mul(mul(A.kappa, Tv[n]), om[n]));
+    }
     vdp[n] = vt1;
     vdp[lf + n] = vt2;
     vgp[n] = tt;
@@ -230,7 +268,8 @@ __global__ void __launch_bounds__(512) caar_strict_kernel(const KernelArgs A) {
       const double a0 = mul(mp, add(v_nm1[n * 2], mul(A.dt2, vdp[n])));
       const double a1 = mul(mp, add(v_nm1[n * 2 + 1], mul(A.dt2, vdp[lf + n])));
       const double a2 = mul(mp, add(T_nm1[n], mul(A.dt2, vgp[n])));
-      const double a3 = mul(mp, sub(dp_nm1[n], mul(A.dt2, divdp[n])));
+      const double dflux = eul ? sub(add(divdp[n], eta[n + PTS]), eta[n]) : divdp[n];  // F/routine_extracted.F90:515-517
+      const double a3 = mul(mp, sub(dp_nm1[n], mul(A.dt2, dflux)));
       v_np1[n * 2] = a0;
       v_np1[n * 2 + 1] = a1;
       T_np1[n] = a2;
@@ -241,7 +280,7 @@ __global__ void __launch_bounds__(512) caar_strict_kernel(const KernelArgs A) {
 
 }  // namespace
 
-size_t strict_smem_bytes(int nlev) { return (size_t)11 * nlev * PTS * sizeof(double); }
+size_t strict_smem_bytes(int nlev) { return ((size_t)12 * nlev + 1) * PTS * sizeof(double); }
 
 cudaError_t launch_strict(const KernelArgs& a, cudaStream_t s) {
   const size_t smem = strict_smem_bytes(a.nlev);
