@@ -231,6 +231,12 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
   return v;
 }
 
+#ifndef CAAR_EUL_REGS
+// register cap of the Eulerian nlev=72 instance. Its live set (dsave, dp, vtens, ttens through the scans) does not
+// fit 96 registers: measured 0.46 of the HBM peak at 96 (2 CTAs/SM, 480 B of spills), 0.55 at 128, 0.61 at 168
+// (1 CTA/SM, no spills) — profiles/README.md.
+#define CAAR_EUL_REGS 168
+#endif
 #ifndef CAAR_CL128
 #define CAAR_CL128 2  // nlev = 128: the column is split over a cluster of two 256-thread CTAs
 #endif
@@ -239,13 +245,15 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 #endif
 
 // register budget per thread for a CTA of `threads` threads: two CTAs per SM where the register file allows it
-constexpr int regs_for(int threads) {
-  return threads <= 256 ? 128                // 2 x 256 x 128 = the whole 64K-register file
+constexpr int regs_for(int threads, bool eul = false) {
+  return (eul && threads > 256 && CAAR_EUL_REGS > 0) ? CAAR_EUL_REGS
+         : threads <= 256 ? 128                // 2 x 256 x 128 = the whole 64K-register file
          : threads <= 320 ? CAAR_REGS_SMALL  // 2 x 288 threads (nlev = 72)
                           : 128;             // one 512-thread CTA per SM
 }
 
-template <int L, int NWT>  // L = levels held by this CTA, NWT = warps per element (scan totals of the whole column)
+// L = levels held by this CTA, NWT = warps per element (scan totals of the whole column), EUL = Eulerian variant
+template <int L, int NWT, bool EUL>
 struct Smem {
   static constexpr int LF = L * PTS;  // doubles per scalar level-field (this CTA's slab)
   // late inputs, overwritten in place by the outputs of the same shape
@@ -257,6 +265,7 @@ struct Smem {
   double Tm1[LF];          // T(nm1)                -> T(np1)
   double Tn0[LF];          // T(n0)   (input only: keeps 8 registers free during the grad-p peak)
   double Qd[LF];           // Qdp     (input only)
+  double vn[EUL ? 2 * LF : 2];  // Eulerian only: v(n0) of the whole slab, for the k-1 / k+1 neighbours of preq_vertadv
   double tot[3][NWT][16];
   // 2x2 tensors: [igp] stride GS = 20 doubles (160 B) instead of 16 so that the four rows read by the
   // four igp-lanes of a level fall into different banks (conflict-free 128-bit broadcast loads)
@@ -271,8 +280,14 @@ struct Smem {
 // CL = 2 is used for nlev = 128: two 256-thread CTAs at 128 registers instead of one 512-thread CTA, so that two
 // CTAs (of different elements, in different phases) share an SM; the vertical scans exchange their per-warp
 // totals through distributed shared memory and a cluster barrier.
-template <int L, int CL>
-__global__ void __launch_bounds__(4 * L / CL) __maxnreg__(regs_for(4 * L / CL))
+// EUL = the Eulerian vertical coordinate (rsplit == 0, F/routine_extracted.F90:227-262,325-334,515-517): after the
+// divergence scan every thread also holds the column total S of div(v dp), hence eta_dot_dpdn at the two interfaces
+// of its level (eta_hi = hybi[k+1]*S - prefix_k, eta_lo = hybi[k]*S - prefix_{k-1}, 0 at the top and the bottom);
+// the levels k-1 and k+1 of T(n0), v(n0) needed by preq_vertadv (LV/CaarFunctor.hpp:504-547) are re-read from
+// global memory (L1/L2 hits: neighbouring threads loaded them), derived_eta_dot_dpdn is updated in place, and the
+// dp3d update moves behind the scan. +259 B per element*level of algorithmic traffic (the eta_dot_dpdn RMW).
+template <int L, int CL, bool EUL>
+__global__ void __launch_bounds__(4 * L / CL) __maxnreg__(regs_for(4 * L / CL, EUL))
 caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ TmaMaps M) {
   constexpr int LC = L / CL;        // levels per CTA
   constexpr int NW = LC / 8;        // warps per CTA
@@ -284,7 +299,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   static_assert(L % (8 * CL) == 0, "a warp holds 8 levels");
   extern __shared__ unsigned char smem_raw[];
   // swizzled TMA tiles need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
-  Smem<LC, NWT>& S = *reinterpret_cast<Smem<LC, NWT>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  Smem<LC, NWT, EUL>& S = *reinterpret_cast<Smem<LC, NWT, EUL>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int t = threadIdx.x;
   const int lane = t & 31, w = t >> 5;
@@ -319,12 +334,13 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
         mbar_expect_tx(&S.xbar[0], XB);
         mbar_expect_tx(&S.xbar[2], XB);
       } else {
-        mbar_expect_tx(&S.xbar[1], XB);
+        mbar_expect_tx(&S.xbar[1], EUL ? 2 * XB : XB);  // Eulerian: rank 1's divergence totals too (column total)
       }
     }
     fence_proxy_async();
-    mbar_expect_tx(&S.bar[2], (A.qn0 != -1 ? 2 : 1) * FB);
+    mbar_expect_tx(&S.bar[2], ((A.qn0 != -1 ? 2 : 1) + (EUL ? 2 : 0)) * FB);
     tma_load(S.Tn0, &M.T, (ie * A.ntl + A.n0) * L + lev0, &S.bar[2]);
+    if (EUL) tma_load(S.vn, &M.v, ((ie * A.ntl + A.n0) * L + lev0) * 2, &S.bar[2]);
     if (A.qn0 != -1) tma_load(S.Qd, &M.Qdp, ((ie * A.qsize_d + 0) * 2 + A.qn0) * L + lev0, &S.bar[2]);
     mbar_expect_tx(&S.bar[0], 4 * FB);
     tma_load(S.vn0, &M.vn0, row_e * 2, &S.bar[0]);
@@ -362,6 +378,8 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   Row dp = ld_row(A.dp3d + on0);
   Row v1, v2;
   ld_row2(A.v + on0 * 2, v1, v2);
+  if (EUL && r == 0)  // this level's derived_eta_dot_dpdn line is read-modify-written after the scans: pull it into L2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.eta_dot_dpdn + e * (size_t)(L + 1) * PTS + off));
 
   // ---- stage the element's geometry
   if (t < 64) {
@@ -508,7 +526,10 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       for (int j = 0; j < 4; ++j) divdp.x[j] = (dudx.x[j] + dvdy.x[j]) * rm.x[j];  // dinv carries rrearth
     }
     // dp3d(np1) = spheremp*(dp3d(nm1) - dt2*divdp)  (PO:254), in place over dp3d(nm1)
-    {
+    Row dsave;  // Eulerian: div(v dp) of this level survives the scan (the vertical flux difference joins it later)
+    if (EUL) {
+      dsave = divdp;
+    } else {
       const Row mp = ld_row(S.mp + r * 4);
       Row o = ld_tile(S.dpm, sw1);
 #pragma unroll
@@ -531,6 +552,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     //   omega_k = (vgrad_p - sum_{l<k} divdp_l - divdp_k/2) / p                 (PO:314-352)
     Row a, ph;
     {
+      Row tq;
       const Row phis = ld_row(S.phis + r * 4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -539,16 +561,17 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
         const double sd = scan_down(divdp.x[j], lane);
         ph.x[j] = phis.x[j] + (sq - 0.5 * q);
         a.x[j] = rp.x[j] * (vgp.x[j] - (sd - 0.5 * divdp.x[j]));
-        dp.x[j] = sq;      // reuse: warp totals live in the end lanes
+        tq.x[j] = sq;      // warp totals live in the end lanes
         divdp.x[j] = sd;
       }
       if (lane < 4) {
-        st_row(&S.tot[1][gw][r * 4], dp);
-        if (CL > 1 && rank == 1) st_row_async_remote(&S.tot[1][gw][r * 4], &S.xbar[1], 0u, dp.x);
+        st_row(&S.tot[1][gw][r * 4], tq);
+        if (CL > 1 && rank == 1) st_row_async_remote(&S.tot[1][gw][r * 4], &S.xbar[1], 0u, tq.x);
       }
       if (lane >= 28) {
         st_row(&S.tot[2][gw][r * 4], divdp);
         if (CL > 1 && rank == 0) st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[2], 1u, divdp.x);
+        if (CL > 1 && rank == 1 && EUL) st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[1], 0u, divdp.x);
       }
     }
     // T tendency with the omega carry factored out: ttens = kappa*T_v*omega - v.gradT, omega = a - rp*carry
@@ -563,7 +586,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     if (CL > 1) mbar_wait(&S.xbar[rank == 0 ? 1 : 2], 0);  // the peer's totals have landed
     if (t == 0) {
       tma_store(&M.vn0, row_e * 2, S.vn0);
-      tma_store(&M.dp3d, row_np1, S.dpm);
+      if (!EUL) tma_store(&M.dp3d, row_np1, S.dpm);
       bulk_commit();
     }
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
@@ -584,6 +607,84 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     // ---- late inputs, second batch (omega_p, T(nm1), v(nm1))
     mbar_wait(&S.bar[1], 0);
     const Row mp = ld_row(S.mp + r * 4);
+    if (EUL) {
+      // column total S of div(v dp) and the vertical mass flux at this level's two interfaces
+      // (F/routine_extracted.F90:233-254): eta(k+1) = hybi(k+1)*S - sum_{l<=k} divdp_l, 0 at the top and bottom
+      double S4[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int ww = 0; ww < NWT; ++ww) {
+        const Row c = ld_row(&S.tot[2][ww][r * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) S4[j] += c.x[j];
+      }
+      const int kg = lev0 + (t >> 2);
+      const double hb_lo = A.hybi[kg], hb_hi = A.hybi[kg + 1];
+      Row ehi, elo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double P = cd[j] + divdp.x[j];  // inclusive prefix of div(v dp)
+        ehi.x[j] = (kg == L - 1) ? 0.0 : fma(hb_hi, S4[j], -P);
+        elo.x[j] = (kg == 0) ? 0.0 : fma(hb_lo, S4[j], -(P - dsave.x[j]));
+      }
+      {  // dp3d(np1) = spheremp*(dp3d(nm1) - dt2*(divdp + eta(k+1) - eta(k)))  (F/routine_extracted.F90:515-517)
+        Row o = ld_tile(S.dpm, sw1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.x[j] = mp.x[j] * fma(-A.dt2, (dsave.x[j] + ehi.x[j]) - elo.x[j], o.x[j]);
+        st_tile(S.dpm, sw1, o);
+      }
+      if (kg > 0) {  // derived_eta_dot_dpdn(k) += eta_ave_w*eta(k) (F:270-277); interfaces 0 and L carry no flux
+        double* pe = A.eta_dot_dpdn + e * (size_t)(L + 1) * PTS + off;
+        Row x = ld_row(pe);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x.x[j] = fma(A.eta_ave_w, elo.x[j], x.x[j]);
+        st_row(pe, x);
+      }
+      // preq_vertadv (LV/CaarFunctor.hpp:504-547): fac+ = eta(k+1)/(2 dp), fac- = eta(k)/(2 dp); the one-sided
+      // forms at the top and bottom follow from eta = 0 there
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double hr = 0.5 * fast_rcp(dp.x[j]);
+        ehi.x[j] *= hr;
+        elo.x[j] *= hr;
+      }
+      // neighbouring levels come from the shared-memory tiles; only the first / last level of a split column
+      // (CL = 2) reads its neighbour, which lives in the peer CTA, from global memory
+      const int kl = t >> 2;  // level inside this CTA's slab
+      {
+        const Row Tk = ld_tile(S.Tn0, sw1);
+        Row Tu = Tk, Td = Tk;
+        if (kg + 1 < L) {
+          if (kl + 1 < LC) Tu = ld_tile(S.Tn0, (uint32_t)(kl + 1) * 128u + ((uint32_t)((2 * r) ^ ((kl + 1) & 7)) << 4));
+          else Tu = ld_row(A.T + on0 + PTS);
+        }
+        if (kg > 0) {
+          if (kl > 0) Td = ld_tile(S.Tn0, (uint32_t)(kl - 1) * 128u + ((uint32_t)((2 * r) ^ ((kl - 1) & 7)) << 4));
+          else Td = ld_row(A.T + on0 - PTS);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)  // ttens = -T_vadv - v.gradT + kappa*T_v*omega (F:333)
+          tta.x[j] -= fma(ehi.x[j], Tu.x[j] - Tk.x[j], elo.x[j] * (Tk.x[j] - Td.x[j]));
+      }
+      {
+        Row uk, vk, uu, vu, ud, vd;
+        ld_tile2(S.vn, sw2, uk, vk);
+        uu = uk; vu = vk; ud = uk; vd = vk;
+        const int tr = t >> 1;  // this thread's row in the (u,v) tile; a level spans two tile rows
+        if (kg + 1 < L) {
+          if (kl + 1 < LC) ld_tile2(S.vn, (uint32_t)(tr + 2) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((tr + 2) & 7)) << 4), uu, vu);
+          else ld_row2(A.v + (on0 + PTS) * 2, uu, vu);
+        }
+        if (kg > 0) {
+          if (kl > 0) ld_tile2(S.vn, (uint32_t)(tr - 2) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((tr - 2) & 7)) << 4), ud, vd);
+          else ld_row2(A.v + (on0 - PTS) * 2, ud, vd);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // vtens = -v_vadv + ... (F:325-331)
+          vt1.x[j] -= fma(ehi.x[j], uu.x[j] - uk.x[j], elo.x[j] * (uk.x[j] - ud.x[j]));
+          vt2.x[j] -= fma(ehi.x[j], vu.x[j] - vk.x[j], elo.x[j] * (vk.x[j] - vd.x[j]));
+        }
+      }
+    }
     {  // derived_omega_p += eta_ave_w*omega (PO:173); T(np1) = spheremp*(T(nm1) + dt2*ttens) (PO:253)
       Row om = ld_tile(S.omp, sw1), Tn = ld_tile(S.Tm1, sw1);
 #pragma unroll
@@ -617,8 +718,16 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     }
   }
   fence_proxy_async();
-  __syncthreads();  // (3) all output tiles complete
+  // (3) all output tiles complete. Eulerian + split column + np1 == n0: the peer CTA reads my boundary level of
+  // T(n0)/v(n0) from global memory, so my stores over that time level must wait for it as well
+  if (CL > 1 && EUL && A.np1 == A.n0) {
+    cluster_arrive();
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
   if (t == 0) {
+    if (EUL) tma_store(&M.dp3d, row_np1, S.dpm);
     tma_store(&M.omega_p, row_e, S.omp);
     tma_store(&M.T, row_np1, S.Tm1);
     tma_store(&M.phi, row_e, S.pec);
@@ -628,16 +737,16 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   }
 }
 
-template <int L, int CL>
+template <int L, int CL, bool EUL>
 cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   const int n = a.nete - a.nets;
   if (n <= 0) return cudaSuccess;
-  constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8>) + 1024;
+  constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8, EUL>) + 1024;
   // per device (function attributes are per context): cheap enough to set on every launch
-  cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) return e;
   // ask for the largest shared-memory carveout so that two ~80 KB CTAs are resident per SM
-  e = cudaFuncSetAttribute(caar_fused_kernel<L, CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   if (!a.tma) return cudaErrorInvalidValue;
@@ -653,7 +762,7 @@ cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, caar_fused_kernel<L, CL>, a, *static_cast<const TmaMaps*>(a.tma));
+  return cudaLaunchKernelEx(&cfg, caar_fused_kernel<L, CL, EUL>, a, *static_cast<const TmaMaps*>(a.tma));
 }
 
 }  // namespace
@@ -704,7 +813,7 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   return 0;
 }
 
-bool fused_supports_eulerian(int) { return false; }
+bool fused_supports_eulerian(int nlev) { return nlev == 72 || nlev == 128; }
 
 bool fused_supports(int nlev) { return nlev == 72 || nlev == 128 || fused_ldg_supports(nlev); }
 
@@ -719,8 +828,8 @@ cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
   // Sweeps: profiles/README.md.
   a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : (a.nlev == 128 ? 16 : 148));
   switch (a.nlev) {
-    case 72: return launch_L<72, 1>(a, s);
-    case 128: return launch_L<128, CAAR_CL128>(a, s);
+    case 72: return a.rsplit == 0 ? launch_L<72, 1, true>(a, s) : launch_L<72, 1, false>(a, s);
+    case 128: return a.rsplit == 0 ? launch_L<128, CAAR_CL128, true>(a, s) : launch_L<128, CAAR_CL128, false>(a, s);
   }
   return launch_fused_ldg(a, s);
 }
