@@ -237,6 +237,9 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 // (1 CTA/SM, no spills) — profiles/README.md.
 #define CAAR_EUL_REGS 168
 #endif
+#ifndef CAAR_PARK
+#define CAAR_PARK 1
+#endif
 #ifndef CAAR_CL128
 #define CAAR_CL128 2  // nlev = 128: the column is split over a cluster of two 256-thread CTAs
 #endif
@@ -252,8 +255,13 @@ constexpr int regs_for(int threads, bool eul = false) {
                           : 128;             // one 512-thread CTA per SM
 }
 
+// Park the two velocity-tendency rows in shared memory through the scan phase (instead of letting the compiler spill
+// them to local memory)? Each thread reuses its OWN 32 bytes of the T(n0) and Qdp input tiles, which it alone reads
+// and which are dead by then — no extra shared memory. Only where registers are short: nlev=72 Lagrangian.
+__host__ __device__ constexpr bool park_for(int L, int CL, bool eul) { return CAAR_PARK && L == 72 && CL == 1 && !eul; }
+
 // L = levels held by this CTA, NWT = warps per element (scan totals of the whole column), EUL = Eulerian variant
-template <int L, int NWT, bool EUL>
+template <int L, int NWT, bool EUL, bool PARK = false>
 struct Smem {
   static constexpr int LF = L * PTS;  // doubles per scalar level-field (this CTA's slab)
   // late inputs, overwritten in place by the outputs of the same shape
@@ -299,7 +307,8 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   static_assert(L % (8 * CL) == 0, "a warp holds 8 levels");
   extern __shared__ unsigned char smem_raw[];
   // swizzled TMA tiles need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
-  Smem<LC, NWT, EUL>& S = *reinterpret_cast<Smem<LC, NWT, EUL>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  constexpr bool PARK = park_for(L, CL, EUL);
+  Smem<LC, NWT, EUL, PARK>& S = *reinterpret_cast<Smem<LC, NWT, EUL, PARK>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int t = threadIdx.x;
   const int lane = t & 31, w = t >> 5;
@@ -494,6 +503,10 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       const Row a = deriv_i(T, cx), b = deriv_j(T, A.dvv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) ttp.x[j] = -fma(a.x[j], w1.x[j], b.x[j] * w2.x[j]);
+    }
+    if (PARK) {  // vtens (without grad Ephi) is not needed before the end of the kernel
+      st_tile(S.Tn0, sw1, vt1);
+      st_tile(S.Qd, sw1, vt2);
     }
 
     // ---- late inputs, first batch (vn0, dp3d(nm1), pecnd) must have landed
@@ -709,6 +722,10 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       gradient(kep, S.dinv + r * GS, cx, A.dvv, g0, g1);
       Row a0, a1;
       ld_tile2(S.vm1, sw2, a0, a1);
+      if (PARK) {
+        vt1 = ld_tile(S.Tn0, sw1);
+        vt2 = ld_tile(S.Qd, sw1);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         a0.x[j] = mp.x[j] * fma(A.dt2, vt1.x[j] - g0.x[j], a0.x[j]);
@@ -741,7 +758,7 @@ template <int L, int CL, bool EUL>
 cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   const int n = a.nete - a.nets;
   if (n <= 0) return cudaSuccess;
-  constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8, EUL>) + 1024;
+  constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8, EUL, park_for(L, CL, EUL)>) + 1024;
   // per device (function attributes are per context): cheap enough to set on every launch
   cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   if (e != cudaSuccess) return e;
@@ -750,6 +767,13 @@ cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
                            (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   if (!a.tma) return cudaErrorInvalidValue;
+  static const bool debug_occ = getenv("CAAR_DEBUG_OCC") != nullptr;
+  if (debug_occ) {
+    int nb = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, caar_fused_kernel<L, CL, EUL>, 4 * L / CL, SMEM);
+    fprintf(stderr, "[caar] caar_fused_kernel<%d,%d,%d>: %d threads, %d B dynamic smem -> %d CTAs/SM\n", L, CL, (int)EUL,
+            4 * L / CL, SMEM, nb);
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n * CL, 1, 1);
   cfg.blockDim = dim3(4 * L / CL, 1, 1);
