@@ -36,6 +36,8 @@ if ROOT not in sys.path:
 METRIC = "compute_and_apply_rhs_elem_lev_updates_per_s"
 UNIT = "elem*lev updates/s"
 NE120 = 86400
+# (elements, nlev) of the BASELINE.json configs, for the workload label
+WORKLOADS = {(5400, 72): "ne=30", (86400, 72): "ne=120", (393216, 128): "ne=256", (49152, 128): "ne=256 / 8"}
 
 
 def b_alg(nlev: int) -> float:
@@ -220,6 +222,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nelem", type=int, default=NE120, help="elements per GPU (default ne=120: 86400)")
     ap.add_argument("--nlev", type=int, default=72)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --nelem elements per GPU (default); strong: --nelem elements in total, cut into "
+                         "contiguous blocks per rank (BASELINE configs[3]/[4] strong-scaling variants)")
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-chunk", type=int, default=0, help="elements per pipeline chunk (0 = automatic)")
@@ -258,7 +263,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    E, L = args.nelem, args.nlev
+    L = args.nlev
+    if args.scaling == "strong":
+        from tinman_sandbox_b200.partition import element_range
+        lo, hi = element_range(rank, world, args.nelem)
+        E, elem_offset, E_total = hi - lo, lo, args.nelem
+    else:
+        E, elem_offset, E_total = args.nelem, rank * args.nelem, world * args.nelem
     mode = tb.MODE_FAST if args.mode == "fast" else tb.MODE_STRICT
 
     # ---- synthetic inputs: the reference's closed-form init for this rank's element range, in pinned memory
@@ -284,7 +295,7 @@ def main():
     if not pin_ok:
         def alloc(shape):  # noqa: F811
             return np.zeros(shape, dtype=np.float64)
-    td = TestData(E, L, alloc=alloc).init_data(elem_offset=rank * E)
+    td = TestData(E, L, alloc=alloc).init_data(elem_offset=elem_offset)
     h = tb.Caar(E, L, device=local_rank)
     h.set_params(td.consts, td.dvv, td.ps0, td.hyai)
     h.set_control(*[int(x) for x in td.ctl], dt2=td.dt2)
@@ -310,7 +321,7 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     ms_per_step = ms_max / args.steps
-    value = world * E * L * args.steps / (ms_max * 1e-3)
+    value = E_total * L * args.steps / (ms_max * 1e-3)
 
     # ---- norms: the only collective of the job (sum of squares all-reduced over NVLink, then sqrt)
     ss = torch.from_numpy(h.sumsq(int(td.ctl[3]))).to(dev)
@@ -335,7 +346,7 @@ def main():
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dt = float(t_e.item())
-        e2e = {"value": world * E * L * args.e2e_steps / dt, "unit": UNIT,
+        e2e = {"value": E_total * L * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * dt / args.e2e_steps,
                "pcie_gbs": {"h2d": h2d * args.e2e_steps / dt / 1e9, "d2h": d2h * args.e2e_steps / dt / 1e9},
@@ -362,9 +373,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference closed-form init)",
-            "config": {"workload": f"ne=120 cubed sphere: {E} elements per GPU, np=4, nlev={L}, FP64, "
+            "config": {"workload": f"{WORKLOADS.get((E_total // (world if args.scaling == 'weak' else 1), L), 'cubed sphere')}: "
+                                   f"{E} elements per GPU ({E_total} in total), np=4, nlev={L}, FP64, "
                                    f"n0/np1/nm1 distinct, qn0=0",
                        "elements_per_gpu": E, "nlev": L, "mode": args.mode, "host_cpus_bound": numa,
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" %
