@@ -463,7 +463,26 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
 
     // ---- B1: grad_p; vgrad_p (PO:103-112); C: T_v (PO:126-156); glnps folded into the v tendencies
     Row gp0, gp1;
-    gradient(p, S.dinv + r * GS, cx, A.dvv, gp0, gp1);
+    // w = Dinv.v: v.grad(s) = a_s*w1 + b_s*w2 with (a_s,b_s) the raw igp/jgp derivatives of s
+    // (PO/sphere_operators.cpp:21-47), and the divergence flux is metdet*dp*w (PO/sphere_operators.cpp:62-72): one
+    // pass over Dinv serves -v.grad T (PO:200-209) and divergence_sphere(v*dp) (PO:122). Where registers allow
+    // (the 128-register instances) the same pass also produces grad p; at 96 registers that costs more in spill
+    // reloads than the 8 LDS.128 it saves (measured 0.845 vs 0.891), so w is formed later there.
+    constexpr bool FUSE_W = (CL > 1);
+    Row w1, w2;
+    if constexpr (FUSE_W) {
+      const Row a = deriv_i(p, cx), b = deriv_j(p, A.dvv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 d01 = lds2(S.dinv + r * GS + j * 4), d23 = lds2(S.dinv + r * GS + j * 4 + 2);
+        gp0.x[j] = fma(d01.x, a.x[j], d23.x * b.x[j]);
+        gp1.x[j] = fma(d01.y, a.x[j], d23.y * b.x[j]);
+        w1.x[j] = fma(d01.x, v1.x[j], d01.y * v2.x[j]);
+        w2.x[j] = fma(d23.x, v1.x[j], d23.y * v2.x[j]);
+      }
+    } else {
+      gradient(p, S.dinv + r * GS, cx, A.dvv, gp0, gp1);
+    }
     // from here on p is dead; only rp is kept
     mbar_wait(&S.bar[2], 0);  // T(n0), Qdp tiles
     Row Tv = ld_tile(S.Tn0, sw1);
@@ -487,15 +506,13 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     Row& vgp = p;
     asm volatile("" ::: "memory");
 
-    // ---- w = Dinv.v: v.grad(s) = a_s*w1 + b_s*w2 with (a_s,b_s) the raw igp/jgp derivatives of s
-    // (PO/sphere_operators.cpp:21-47), and the divergence flux is metdet*dp*w (PO/sphere_operators.cpp:62-72):
-    // one pass over Dinv serves -v.grad T (PO:200-209) and divergence_sphere(v*dp) (PO:122)
-    Row w1, w2;
+    if constexpr (!FUSE_W) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double2 d01 = lds2(S.dinv + r * GS + j * 4), d23 = lds2(S.dinv + r * GS + j * 4 + 2);
-      w1.x[j] = fma(d01.x, v1.x[j], d01.y * v2.x[j]);
-      w2.x[j] = fma(d23.x, v1.x[j], d23.y * v2.x[j]);
+      for (int j = 0; j < 4; ++j) {
+        const double2 d01 = lds2(S.dinv + r * GS + j * 4), d23 = lds2(S.dinv + r * GS + j * 4 + 2);
+        w1.x[j] = fma(d01.x, v1.x[j], d01.y * v2.x[j]);
+        w2.x[j] = fma(d23.x, v1.x[j], d23.y * v2.x[j]);
+      }
     }
     Row ttp;
     {
