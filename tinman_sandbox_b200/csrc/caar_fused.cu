@@ -237,6 +237,32 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 // (1 CTA/SM, no spills) — profiles/README.md.
 #define CAAR_EUL_REGS 168
 #endif
+// Sum over the warps ww in [lo, hi) of the per-warp scan totals tot[ww][r*4 + j], j = 0..3, delivered to every lane
+// for its own GLL row r. Lane (q = lane/4, r) loads rows q, q+8, ... and the eight partial sums of a row meet in a
+// butterfly over the lane bits 2..4: 2*NWT/8 LDS.128 + 24 SHFL per call instead of up to 2*NWT LDS.128 per thread.
+// Pays when the column has 16 warps (nlev = 128) or when the column total is needed too (Eulerian instances); at 9
+// warps (nlev = 72, Lagrangian) the plain loop is as cheap.
+template <int NWT>
+__device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int hi, int lane, double (&out)[4]) {
+  const int q = lane >> 2, r = lane & 3;
+  double acc[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int base = 0; base < NWT; base += 8) {
+    const int ww = base + q;
+    if (ww < NWT && ww >= lo && ww < hi) {
+      const Row c = ld_row(&tot[ww][r * 4]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += c.x[j];
+    }
+  }
+#pragma unroll
+  for (int d = 4; d < 32; d <<= 1)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(FULL, acc[j], d);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = acc[j];
+}
+
 #ifndef CAAR_PARK
 #define CAAR_PARK 1
 #endif
@@ -428,14 +454,21 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     }
     __syncthreads();  // (1) tot[0], geometry, mbarrier init visible
     if (CL > 1 && rank == 1) mbar_wait(&S.xbar[0], 0);  // rank 0's totals have landed
+    // see warp_totals(): A/B nlev=128 0.831 -> 0.844 (Eulerian 0.575 -> 0.674); nlev=72 0.902 -> 0.899 (Eulerian,
+    // which also needs the column total, 0.607 -> 0.630)
+    constexpr bool LANE_CARRY = (NWT >= 16) || EUL;
     double carry[4] = {0, 0, 0, 0};
+    if constexpr (LANE_CARRY) {
+      warp_totals<NWT>(S.tot[0], 0, gw, lane, carry);
+    } else {
 #pragma unroll
-    for (int ww = 0; ww < NWT - 1; ++ww)
-      if (ww < gw) {
-        const Row c = ld_row(&S.tot[0][ww][r * 4]);
+      for (int ww = 0; ww < NWT - 1; ++ww)
+        if (ww < gw) {
+          const Row c = ld_row(&S.tot[0][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) carry[j] += c.x[j];
-      }
+          for (int j = 0; j < 4; ++j) carry[j] += c.x[j];
+        }
+    }
     const double ptop = A.hyai0 * A.ps0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -620,17 +653,22 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       bulk_commit();
     }
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
+    if constexpr (LANE_CARRY) {
+      warp_totals<NWT>(S.tot[1], gw + 1, NWT, lane, cq);
+      warp_totals<NWT>(S.tot[2], 0, gw, lane, cd);
+    } else {
 #pragma unroll
-    for (int ww = 0; ww < NWT; ++ww) {
-      if (ww > gw) {
-        const Row c = ld_row(&S.tot[1][ww][r * 4]);
+      for (int ww = 0; ww < NWT; ++ww) {
+        if (ww > gw) {
+          const Row c = ld_row(&S.tot[1][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cq[j] += c.x[j];
-      }
-      if (ww < gw) {
-        const Row c = ld_row(&S.tot[2][ww][r * 4]);
+          for (int j = 0; j < 4; ++j) cq[j] += c.x[j];
+        }
+        if (ww < gw) {
+          const Row c = ld_row(&S.tot[2][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cd[j] += c.x[j];
+          for (int j = 0; j < 4; ++j) cd[j] += c.x[j];
+        }
       }
     }
 
@@ -641,11 +679,15 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       // column total S of div(v dp) and the vertical mass flux at this level's two interfaces
       // (F/routine_extracted.F90:233-254): eta(k+1) = hybi(k+1)*S - sum_{l<=k} divdp_l, 0 at the top and bottom
       double S4[4] = {0, 0, 0, 0};
+      if constexpr (LANE_CARRY) {
+        warp_totals<NWT>(S.tot[2], 0, NWT, lane, S4);
+      } else {
 #pragma unroll
-      for (int ww = 0; ww < NWT; ++ww) {
-        const Row c = ld_row(&S.tot[2][ww][r * 4]);
+        for (int ww = 0; ww < NWT; ++ww) {
+          const Row c = ld_row(&S.tot[2][ww][r * 4]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) S4[j] += c.x[j];
+          for (int j = 0; j < 4; ++j) S4[j] += c.x[j];
+        }
       }
       const int kg = lev0 + (t >> 2);
       const double hb_lo = A.hybi[kg], hb_hi = A.hybi[kg + 1];
