@@ -299,7 +299,7 @@ struct Smem {
   double Tm1[LF];          // T(nm1)                -> T(np1)
   double Tn0[LF];          // T(n0)   (input only: keeps 8 registers free during the grad-p peak)
   double Qd[LF];           // Qdp     (input only)
-  double vn[EUL ? 2 * LF : 2];  // Eulerian only: v(n0) of the whole slab, for the k-1 / k+1 neighbours of preq_vertadv
+  double vn[EUL ? 2 * LF : 2];  // Eulerian only (last tile: nothing behind it needs the 1024-byte tile alignment): v(n0) of the whole slab, for the k-1 / k+1 neighbours of preq_vertadv
   double tot[3][NWT][16];
   // 2x2 tensors: [igp] stride GS = 20 doubles (160 B) instead of 16 so that the four rows read by the
   // four igp-lanes of a level fall into different banks (conflict-free 128-bit broadcast loads)
