@@ -81,6 +81,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // Store a row into the same shared-memory location of CTA `rank` of this cluster (distributed shared memory) and
@@ -266,6 +267,9 @@ __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int
 #ifndef CAAR_PARK
 #define CAAR_PARK 1
 #endif
+#ifndef CAAR_CL72
+#define CAAR_CL72 3   // nlev = 72: the column is split over a cluster of three 96-thread CTAs (24 levels each)
+#endif
 #ifndef CAAR_CL128
 #define CAAR_CL128 2  // nlev = 128: the column is split over a cluster of two 256-thread CTAs
 #endif
@@ -307,7 +311,7 @@ struct Smem {
   double dmat[4 * 20];     // D
   double met[16], rmet[16], fcor[16], mp[16], phis[16];
   uint64_t bar[3];
-  uint64_t xbar[3];  // CL = 2: arrival of the peer CTA's scan totals tot[0], tot[1], tot[2]
+  uint64_t xbar[3];  // CL > 1: arrival of the peer CTAs' scan totals tot[0], tot[1], tot[2]
 };
 
 // L = levels of the element, CL = CTAs per element (a thread-block cluster of CL CTAs, each holding L/CL levels).
@@ -331,7 +335,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   constexpr int GS = 20;  // padded igp stride of the 2x2 tensors in shared memory
   constexpr unsigned FB = LF * sizeof(double);  // bytes of one scalar level-field slab
   static_assert(L % (8 * CL) == 0, "a warp holds 8 levels");
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   // swizzled TMA tiles need 1024-byte alignment; the launch adds 1 KB of slack for this round-up
   constexpr bool PARK = park_for(L, CL, EUL);
   Smem<LC, NWT, EUL, PARK>& S = *reinterpret_cast<Smem<LC, NWT, EUL, PARK>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -365,14 +369,21 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       mbar_init(&S.xbar[1], 1);
       mbar_init(&S.xbar[2], 1);
       fence_mbar_init_cluster();
-      if (rank == 1) {
-        mbar_expect_tx(&S.xbar[0], XB);
-        mbar_expect_tx(&S.xbar[2], XB);
-      } else {
-        mbar_expect_tx(&S.xbar[1], EUL ? 2 * XB : XB);  // Eulerian: rank 1's divergence totals too (column total)
+      // forward totals (pressure, divergence) come from every lower rank, reverse totals (geopotential) from every
+      // higher rank; Eulerian: the higher ranks' divergence totals too (column total)
+      if (rank > 0) {
+        mbar_expect_tx(&S.xbar[0], rank * XB);
+        mbar_expect_tx(&S.xbar[2], rank * XB);
       }
+      if (rank + 1 < CL) mbar_expect_tx(&S.xbar[1], (CL - 1 - rank) * (EUL ? 2 * XB : XB));
     }
     fence_proxy_async();
+  }
+  // "my mbarriers are initialised" — the peer may send to me once it has waited on this. Relaxed: the
+  // fence.mbarrier_init above is the release; a releasing arrive placed after the TMA issue below would wait for
+  // every outstanding bulk copy (measured: 22 % of all stall samples on ERRBAR / UCGABAR_ARV).
+  if (CL > 1) cluster_arrive_relaxed();
+  if (t == 0) {
     mbar_expect_tx(&S.bar[2], ((A.qn0 != -1 ? 2 : 1) + (EUL ? 2 : 0)) * FB);
     tma_load(S.Tn0, &M.T, (ie * A.ntl + A.n0) * L + lev0, &S.bar[2]);
     if (EUL) tma_load(S.vn, &M.v, ((ie * A.ntl + A.n0) * L + lev0) * 2, &S.bar[2]);
@@ -405,8 +416,6 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       }
     }
   }
-
-  if (CL > 1) cluster_arrive();  // "my mbarriers are initialised" — the peer may send to me once it has waited on this
 
   // ---- early inputs straight to registers
   const size_t on0 = (e * A.ntl + A.n0) * lf + off;
@@ -450,10 +459,11 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     if (CL > 1) cluster_wait();  // the peer CTA is running and has initialised its mbarriers
     if (lane >= 28) {
       st_row(&S.tot[0][gw][r * 4], p);
-      if (CL > 1 && rank == 0) st_row_async_remote(&S.tot[0][gw][r * 4], &S.xbar[0], 1u, p.x);
+      if (CL > 1)
+        for (uint32_t rr = rank + 1; rr < (uint32_t)CL; ++rr) st_row_async_remote(&S.tot[0][gw][r * 4], &S.xbar[0], rr, p.x);
     }
     __syncthreads();  // (1) tot[0], geometry, mbarrier init visible
-    if (CL > 1 && rank == 1) mbar_wait(&S.xbar[0], 0);  // rank 0's totals have landed
+    if (CL > 1 && rank > 0) mbar_wait(&S.xbar[0], 0);  // the lower ranks' totals have landed
     // see warp_totals(): A/B nlev=128 0.831 -> 0.844 (Eulerian 0.575 -> 0.674); nlev=72 0.902 -> 0.899 (Eulerian,
     // which also needs the column total, 0.607 -> 0.630)
     constexpr bool LANE_CARRY = (NWT >= 16) || EUL;
@@ -629,12 +639,17 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       }
       if (lane < 4) {
         st_row(&S.tot[1][gw][r * 4], tq);
-        if (CL > 1 && rank == 1) st_row_async_remote(&S.tot[1][gw][r * 4], &S.xbar[1], 0u, tq.x);
+        if (CL > 1)
+          for (uint32_t rr = 0; rr < rank; ++rr) st_row_async_remote(&S.tot[1][gw][r * 4], &S.xbar[1], rr, tq.x);
       }
       if (lane >= 28) {
         st_row(&S.tot[2][gw][r * 4], divdp);
-        if (CL > 1 && rank == 0) st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[2], 1u, divdp.x);
-        if (CL > 1 && rank == 1 && EUL) st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[1], 0u, divdp.x);
+        if (CL > 1) {
+          for (uint32_t rr = rank + 1; rr < (uint32_t)CL; ++rr)
+            st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[2], rr, divdp.x);
+          if (EUL)
+            for (uint32_t rr = 0; rr < rank; ++rr) st_row_async_remote(&S.tot[2][gw][r * 4], &S.xbar[1], rr, divdp.x);
+        }
       }
     }
     // T tendency with the omega carry factored out: ttens = kappa*T_v*omega - v.gradT, omega = a - rp*carry
@@ -646,7 +661,10 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       ttb.x[j] = kt * rp.x[j];
     }
     __syncthreads();  // (2) scan totals visible; vn0 / dp3d(np1) tiles complete
-    if (CL > 1) mbar_wait(&S.xbar[rank == 0 ? 1 : 2], 0);  // the peer's totals have landed
+    if (CL > 1) {  // the peers' totals have landed
+      if (rank + 1 < CL) mbar_wait(&S.xbar[1], 0);
+      if (rank > 0) mbar_wait(&S.xbar[2], 0);
+    }
     if (t == 0) {
       tma_store(&M.vn0, row_e * 2, S.vn0);
       if (!EUL) tma_store(&M.dp3d, row_np1, S.dpm);
@@ -863,7 +881,7 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   }
   const encode_t encode = reinterpret_cast<encode_t>(fn);
   const cuuint64_t E = (cuuint64_t)a.nelem, L = (cuuint64_t)a.nlev, ntl = (cuuint64_t)a.ntl;
-  const cuuint32_t LB = (cuuint32_t)(a.nlev == 128 ? a.nlev / CAAR_CL128 : a.nlev);  // levels per CTA = box rows
+  const cuuint32_t LB = (cuuint32_t)(a.nlev / (a.nlev == 128 ? CAAR_CL128 : a.nlev == 72 ? CAAR_CL72 : 1));  // levels per CTA = box rows
   struct Spec { CUtensorMap* m; const void* base; cuuint64_t rows; cuuint32_t box; const char* name; };
   const Spec specs[8] = {
       {&out->Qdp, a.Qdp, E * (cuuint64_t)a.qsize_d * 2 * L, LB, "Qdp"},
@@ -906,12 +924,12 @@ cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
     const char* v = getenv("CAAR_PF_DIST");
     return v ? atoi(v) : -1;
   }();
-  // default distance: nlev=72 -> 148 elements (one CTA per SM ahead; best of an 8...592 sweep at ne=120: 90 % of
-  // the measured peak vs 83 % at 16); nlev=128 (CTA pairs) -> 16 (flat optimum 4...24: 82 %, 74 % at 148).
+  // default distance: nlev=72 (CTA triples) -> 74 elements (16: 0.921, 32: 0.937, 74: 0.946, 148: 0.944 of the
+  // measured peak); nlev=128 (CTA pairs) -> 32 (flat optimum 4...48, 0.74 at 148).
   // Sweeps: profiles/README.md.
-  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : (a.nlev == 128 ? 16 : 148));
+  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : (a.nlev == 128 ? 32 : 74));
   switch (a.nlev) {
-    case 72: return a.rsplit == 0 ? launch_L<72, 1, true>(a, s) : launch_L<72, 1, false>(a, s);
+    case 72: return a.rsplit == 0 ? launch_L<72, CAAR_CL72, true>(a, s) : launch_L<72, CAAR_CL72, false>(a, s);
     case 128: return a.rsplit == 0 ? launch_L<128, CAAR_CL128, true>(a, s) : launch_L<128, CAAR_CL128, false>(a, s);
   }
   return launch_fused_ldg(a, s);
