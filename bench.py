@@ -70,7 +70,7 @@ class ClockSampler:
     (the library behind nvidia-smi) from a background thread every few milliseconds — the timed region of the
     default run lasts ~60 ms, too short for `nvidia-smi -lms`."""
 
-    def __init__(self, gpu_index, period_s=0.004):
+    def __init__(self, gpu_index, period_s=0.002):
         import threading
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._stop = threading.Event()
@@ -106,7 +106,8 @@ class ClockSampler:
                 for n, bit in names:
                     if r & bit:
                         self.reasons.add(n)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0)
+                if len(self.samples) % 8 == 1:      # power is slow to read and slow to change
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0)
             except Exception:
                 pass
             self._stop.wait(self.period)
