@@ -241,8 +241,7 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 // Sum over the warps ww in [lo, hi) of the per-warp scan totals tot[ww][r*4 + j], j = 0..3, delivered to every lane
 // for its own GLL row r. Lane (q = lane/4, r) loads rows q, q+8, ... and the eight partial sums of a row meet in a
 // butterfly over the lane bits 2..4: 2*NWT/8 LDS.128 + 24 SHFL per call instead of up to 2*NWT LDS.128 per thread.
-// Pays when the column has 16 warps (nlev = 128) or when the column total is needed too (Eulerian instances); at 9
-// warps (nlev = 72, Lagrangian) the plain loop is as cheap.
+// Used by every cluster instance (the carry chain of dependent DADDs becomes a 3-step butterfly).
 template <int NWT>
 __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int hi, int lane, double (&out)[4]) {
   const int q = lane >> 2, r = lane & 3;
@@ -464,9 +463,10 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     }
     __syncthreads();  // (1) tot[0], geometry, mbarrier init visible
     if (CL > 1 && rank > 0) mbar_wait(&S.xbar[0], 0);  // the lower ranks' totals have landed
-    // see warp_totals(): A/B nlev=128 0.831 -> 0.844 (Eulerian 0.575 -> 0.674); nlev=72 0.902 -> 0.899 (Eulerian,
-    // which also needs the column total, 0.607 -> 0.630)
-    constexpr bool LANE_CARRY = (NWT >= 16) || EUL;
+    // see warp_totals(). A/B: nlev=128 0.831 -> 0.844 (Eulerian 0.575 -> 0.674); nlev=72 on CTA triples 0.965 -> 0.993
+    // (and no spills left); only the single-CTA nlev=72 instance at 96 registers is better off with the plain loop
+    // (0.902 vs 0.899)
+    constexpr bool LANE_CARRY = (CL > 1) || (NWT >= 16) || EUL;
     double carry[4] = {0, 0, 0, 0};
     if constexpr (LANE_CARRY) {
       warp_totals<NWT>(S.tot[0], 0, gw, lane, carry);
