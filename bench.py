@@ -113,8 +113,9 @@ class ClockSampler:
             self._stop.wait(self.period)
 
     def mark(self):
-        """Samples taken from here on belong to the timed region."""
-        self.t_mark = len(self.samples)
+        """Samples taken from here on belong to the timed region (plus the one in flight: the GPU has been under
+        the same load for two steps when this is called, and an NVML query takes longer than a step)."""
+        self.t_mark = max(0, len(self.samples) - 1)
         self.reasons.clear()
 
     def stop(self):
