@@ -2,28 +2,39 @@
 // ONE kernel and one HBM pass (every input read once, every output written once; all 18 reference
 // temporaries of PO/compute_and_apply_rhs.cpp:18-35 live in registers).
 //
-// Work decomposition ("R4"): one CTA per element, 4*nlev threads. Thread t owns level k = t/4 and GLL row
-// igp = t%4, i.e. the 4 points jgp = 0..3: 32 contiguous bytes of every scalar level-field, 64 of (u,v).
+// Work decomposition: one THREAD-BLOCK CLUSTER per element. The column of nlev levels is cut into CL slabs, one
+// CTA each (nlev = 72: three CTAs of 24 levels / 96 threads; nlev = 128: two CTAs of 64 levels / 256 threads).
+// Thread t of a CTA owns level t/4 of the slab and GLL row igp = t%4, i.e. the 4 points jgp = 0..3: 32 contiguous
+// bytes of every scalar level-field, 64 of (u,v). 128 registers per thread; 5 (nlev=72) or 2 (nlev=128) CTAs of
+// different elements share an SM, each in its own phase.
 //
-// Data movement (per element, nlev=72):
-//   * "early" inputs dp3d(n0), v(n0), T(n0), Qdp — needed at once — are LDG.128'd straight into registers;
-//   * "late" inputs derived_vn0, pecnd, derived_omega_p, dp3d(nm1), T(nm1), v(nm1) (72 KB) are fetched by ONE
-//     thread at kernel entry with six TMA bulk copies (cp.async.bulk, SASS UBLKCP) into shared memory and
-//     complete on two mbarriers while the CTA computes: no registers, no LSU, full prefetch distance;
+// Data movement (per CTA):
+//   * "early" inputs dp3d(n0), v(n0) — needed at once — are LDG.128'd straight into registers;
+//   * T(n0), Qdp and the "late" inputs derived_vn0, pecnd, derived_omega_p, dp3d(nm1), T(nm1), v(nm1) are fetched by
+//     ONE thread at kernel entry with eight 2-D tiled TMA copies (cp.async.bulk.tensor.2d, SASS UTMALDG.2D, 128-byte
+//     swizzle) into shared memory and complete on three mbarriers while the CTA computes: no registers, no LSU, full
+//     prefetch distance;
 //   * every output is written IN PLACE over the late input that has the same shape
 //     (vn0->vn0, pecnd->phi, omega_p->omega_p, dp3d(nm1)->dp3d(np1), T(nm1)->T(np1), v(nm1)->v(np1)) and
-//     leaves the SM as six TMA bulk stores: fully coalesced, asynchronous, no per-thread STG.
+//     leaves the SM as six TMA tile stores (UTMASTG.2D): fully coalesced, asynchronous, no per-thread STG;
 //   * the element's 2-D geometry (Dinv*rrearth, D, metdet, rmetdet, fcor, spheremp, phis: 1664 B) sits in
-//     shared memory and is re-read (warp-broadcast) where used, instead of pinning 40 registers.
+//     shared memory and is re-read (warp-broadcast) where used, instead of pinning 40 registers;
+//   * thread 0 prefetches the early inputs and the geometry of a later element into L2 (cp.async.bulk.prefetch.L2).
 //
 // Math:
 //   * sphere operators (PO/sphere_operators.cpp:9-129): derivative along jgp is thread-local (Dvv from the
 //     constant bank), derivative along igp takes the other three rows of the level from lanes lane^1,2,3.
 //   * vertical integrals (PO:76-97, 280-312, 314-352) in scan form: warp-shuffle scans over the 8 levels of
-//     a warp (lane stride 4) + carry over the nlev/8 warps through shared memory; 3 __syncthreads in all.
+//     a warp (lane stride 4); the per-warp totals are combined over the nlev/8 warps of the column — inside a CTA
+//     through shared memory, between the CTAs of the cluster through distributed shared memory: a warp sends its
+//     total row to the CTAs that need it with st.async ... mbarrier::complete_tx (SASS STAS) and the receiver
+//     waits on its own mbarrier (no cluster barrier, no fence on the critical path). 3 __syncthreads in all.
 //   * one reciprocal of p serves the four divisions by p (PO:219,300,333,336).
 // Rounding differs from the reference by FMA contraction, scan ordering and the shared reciprocal
 // (~1e-15 relative); tests/test_parity_gpu.py holds it to 1e-12 per field.
+//
+// EUL instances: the Eulerian vertical coordinate (rsplit == 0), see the comment at the kernel.
+// CL = 1 (one CTA per element; -DCAAR_CL72=1) is the previous generation of this kernel, kept compilable.
 #include <cstdio>
 #include <cstdlib>
 
@@ -233,7 +244,7 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 }
 
 #ifndef CAAR_EUL_REGS
-// register cap of the Eulerian nlev=72 instance. Its live set (dsave, dp, vtens, ttens through the scans) does not
+// register cap of the single-CTA (CL = 1) Eulerian nlev=72 instance. Its live set (dsave, dp, vtens, ttens through the scans) does not
 // fit 96 registers: measured 0.46 of the HBM peak at 96 (2 CTAs/SM, 480 B of spills), 0.55 at 128, 0.61 at 168
 // (1 CTA/SM, no spills) — profiles/README.md.
 #define CAAR_EUL_REGS 168
@@ -273,15 +284,15 @@ __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int
 #define CAAR_CL128 2  // nlev = 128: the column is split over a cluster of two 256-thread CTAs
 #endif
 #ifndef CAAR_REGS_SMALL
-#define CAAR_REGS_SMALL 96  // 2 CTAs of 9 warps per SM = 5 warps on the fullest SMSP: 16384/(5*32) = 102 -> 96
+#define CAAR_REGS_SMALL 96  // CL = 1, nlev = 72: 2 CTAs of 9 warps per SM = 5 warps on the fullest SMSP: 16384/(5*32) = 102 -> 96
 #endif
 
-// register budget per thread for a CTA of `threads` threads: two CTAs per SM where the register file allows it
+// register budget per thread for a CTA of `threads` threads
 constexpr int regs_for(int threads, bool eul = false) {
-  return (eul && threads > 256 && CAAR_EUL_REGS > 0) ? CAAR_EUL_REGS
-         : threads <= 256 ? 128                // 2 x 256 x 128 = the whole 64K-register file
-         : threads <= 320 ? CAAR_REGS_SMALL  // 2 x 288 threads (nlev = 72)
-                          : 128;             // one 512-thread CTA per SM
+  return (eul && threads > 256 && CAAR_EUL_REGS > 0) ? CAAR_EUL_REGS  // CL = 1 Eulerian: one 288-thread CTA per SM
+         : threads <= 256 ? 128              // cluster CTAs: 5 x 96 or 2 x 256 threads x 128 registers per SM
+         : threads <= 320 ? CAAR_REGS_SMALL  // CL = 1: 2 x 288 threads (nlev = 72)
+                          : 128;             // CL = 1: one 512-thread CTA per SM (nlev = 128)
 }
 
 // Park the two velocity-tendency rows in shared memory through the scan phase (instead of letting the compiler spill
