@@ -14,10 +14,12 @@
 //
 // Work decomposition: levels are independent here (no vertical integral), so the unit of work is one level of one
 // element = 4 threads (thread = GLL row, 4 points each, as in the fused CAAR kernel: derivative along jgp
-// thread-local, along igp through the three other lanes of the level). CTAs of 256 threads take 64 consecutive
-// (element, level) pairs of the flat index space; 3 CTAs per SM. The flux weights w = metdet * Dinv * vstar are
+// thread-local, along igp through the three other lanes of the level). Persistent CTAs of 256 threads walk the flat
+// (element, level) index space in groups of 64 rows with a grid-stride loop; 3 CTAs per SM. The flux weights w = metdet * Dinv * vstar are
 // formed once per level and kept in registers over the tracer loop, which is unrolled by two so that two Qdp rows
 // are in flight per thread.
+#include <cstdlib>
+
 #include "caar_device.cuh"
 
 namespace caar {
@@ -95,31 +97,7 @@ template <bool STRICT>
 __global__ void __launch_bounds__(256, STRICT ? 2 : 3) euler_step_kernel(const __grid_constant__ EulerArgs A) {
   const int t = threadIdx.x, lane = t & 31, r = t & 3;
   const int L = A.nlev;
-  // flat (element, level) index of this group of 4 threads; the tail of the last CTA computes on clamped indices
-  // (the shuffles need every lane) and skips the stores
-  const long long n_rows = (long long)A.nelem_run * L;
-  long long gk = (long long)blockIdx.x * 64 + (t >> 2);
-  const bool live = gk < n_rows;
-  if (!live) gk = n_rows - 1;
-  const size_t e = (size_t)A.nets + (size_t)(gk / L);
-  const int k = (int)(gk % L);
   const size_t lf = (size_t)L * PTS;
-  const size_t off = (size_t)k * PTS + r * 4;
-  // this row's inputs: vstar (u,v), Dinv [jgp][2][2], metdet, rmetdet
-  double u[4], v[4], di[4][4], met[4], rmet[4];
-  {
-    const double* p = A.vstar + (e * lf + off) * 2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double2 a = __ldg(reinterpret_cast<const double2*>(p + 2 * j));
-      u[j] = a.x;
-      v[j] = a.y;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) ld4(A.Dinv + e * 64 + (r * 4 + j) * 4, di[j]);
-  ld4(A.metdet + e * 16 + r * 4, met);
-  ld4(A.rmetdet + e * 16 + r * 4, rmet);
   double cx[4];  // cx[x] = Dvv[r^x][r]
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
@@ -129,34 +107,61 @@ __global__ void __launch_bounds__(256, STRICT ? 2 : 3) euler_step_kernel(const _
     if (r == 3) c = A.dvv[(3 ^ x) * 4 + 3];
     cx[x] = c;
   }
-  double w1[4], w2[4];
-  if (!STRICT) {
+  // persistent CTAs: grid-stride loop over groups of 64 (element, level) rows. The tail group computes on clamped
+  // indices (the shuffles need every lane) and skips the stores.
+  const long long n_rows = (long long)A.nelem_run * L;
+  const long long n_groups = (n_rows + 63) / 64;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    long long gk = grp * 64 + (t >> 2);
+    const bool live = gk < n_rows;
+    if (!live) gk = n_rows - 1;
+    const size_t e = (size_t)A.nets + (size_t)(gk / L);
+    const int k = (int)(gk % L);
+    const size_t off = (size_t)k * PTS + r * 4;
+    // this row's inputs: vstar (u,v), Dinv [jgp][2][2], metdet, rmetdet
+    double u[4], v[4], di[4][4], met[4], rmet[4];
+    {
+      const double* p = A.vstar + (e * lf + off) * 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      w1[j] = met[j] * fma(di[j][0], u[j], di[j][1] * v[j]);
-      w2[j] = met[j] * fma(di[j][2], u[j], di[j][3] * v[j]);
-      rmet[j] *= A.rrearth;
+      for (int j = 0; j < 4; ++j) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p + 2 * j));
+        u[j] = a.x;
+        v[j] = a.y;
+      }
     }
-  }
-  const double* qbase = A.Qdp + (e * A.qsize_d * 2 + A.qn0) * lf + off;  // + iq * 2 * lf
-  double* obase = A.qtens + e * A.qsize_d * lf + off;                    // + iq * lf
-  int iq = 0;
-  for (; iq + 1 < A.qsize; iq += 2) {
-    double qa[4], qb[4], oa[4], ob[4];
-    ld4(qbase + (size_t)iq * 2 * lf, qa);
-    ld4(qbase + (size_t)(iq + 1) * 2 * lf, qb);
-    tracer_row<STRICT>(A, qa, u, v, di, met, rmet, w1, w2, cx, lane, r, oa);
-    tracer_row<STRICT>(A, qb, u, v, di, met, rmet, w1, w2, cx, lane, r, ob);
-    if (live) {
-      st4(obase + (size_t)iq * lf, oa);
-      st4(obase + (size_t)(iq + 1) * lf, ob);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ld4(A.Dinv + e * 64 + (r * 4 + j) * 4, di[j]);
+    ld4(A.metdet + e * 16 + r * 4, met);
+    ld4(A.rmetdet + e * 16 + r * 4, rmet);
+    double w1[4], w2[4];
+    if (!STRICT) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        w1[j] = met[j] * fma(di[j][0], u[j], di[j][1] * v[j]);
+        w2[j] = met[j] * fma(di[j][2], u[j], di[j][3] * v[j]);
+        rmet[j] *= A.rrearth;
+      }
     }
-  }
-  if (iq < A.qsize) {
-    double qa[4], oa[4];
-    ld4(qbase + (size_t)iq * 2 * lf, qa);
-    tracer_row<STRICT>(A, qa, u, v, di, met, rmet, w1, w2, cx, lane, r, oa);
-    if (live) st4(obase + (size_t)iq * lf, oa);
+    const double* qbase = A.Qdp + (e * A.qsize_d * 2 + A.qn0) * lf + off;  // + iq * 2 * lf
+    double* obase = A.qtens + e * A.qsize_d * lf + off;                    // + iq * lf
+    int iq = 0;
+    for (; iq + 1 < A.qsize; iq += 2) {
+      double qa[4], qb[4], oa[4], ob[4];
+      ld4(qbase + (size_t)iq * 2 * lf, qa);
+      ld4(qbase + (size_t)(iq + 1) * 2 * lf, qb);
+      tracer_row<STRICT>(A, qa, u, v, di, met, rmet, w1, w2, cx, lane, r, oa);
+      tracer_row<STRICT>(A, qb, u, v, di, met, rmet, w1, w2, cx, lane, r, ob);
+      if (live) {
+        st4(obase + (size_t)iq * lf, oa);
+        st4(obase + (size_t)(iq + 1) * lf, ob);
+      }
+    }
+    if (iq < A.qsize) {
+      double qa[4], oa[4];
+      ld4(qbase + (size_t)iq * 2 * lf, qa);
+      tracer_row<STRICT>(A, qa, u, v, di, met, rmet, w1, w2, cx, lane, r, oa);
+      if (live) st4(obase + (size_t)iq * lf, oa);
+    }
   }
 }
 
@@ -171,7 +176,10 @@ cudaError_t launch_euler_step(const KernelArgs& a, const double* vstar, double* 
   e.dt = dt; e.rrearth = a.rrearth;
   for (int i = 0; i < 16; ++i) e.dvv[i] = a.dvv[i];
   const long long rows = (long long)(nete - nets) * a.nlev;
-  const unsigned blocks = (unsigned)((rows + 63) / 64);
+  long long groups = (rows + 63) / 64;
+  static const int waves = [] { const char* v = getenv("CAAR_EULER_WAVES"); return v ? atoi(v) : 2; }();
+  const long long cap = 148LL * 3 * (waves > 0 ? waves : 1);  // persistent CTAs: a few waves of 3 resident CTAs per SM
+  const unsigned blocks = (unsigned)(waves > 0 && groups > cap ? cap : groups);
   if (strict)
     euler_step_kernel<true><<<blocks, 256, 0, s>>>(e);
   else
