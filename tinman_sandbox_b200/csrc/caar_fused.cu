@@ -579,6 +579,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       st_tile(S.Tn0, sw1, vt1);
       st_tile(S.Qd, sw1, vt2);
     }
+    if (EUL) st_tile(S.Qd, sw1, vt2);  // Eulerian: T(n0) stays in use (vertical neighbours), the Qdp slot is free
 
     // ---- late inputs, first batch (vn0, dp3d(nm1), pecnd) must have landed
     mbar_wait(&S.bar[0], 0);
@@ -628,6 +629,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       const Row pec = ld_tile(S.pec, sw1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) kep.x[j] = fma(0.5, fma(v1.x[j], v1.x[j], v2.x[j] * v2.x[j]), pec.x[j]);
+      if (EUL) st_tile(S.pec, sw1, kep);  // Eulerian: waits in this thread's own (now dead) pecnd slot for phi
     }
     // v1, v2 are dead from here
 
@@ -705,6 +707,24 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     mbar_wait(&S.bar[1], 0);
     const Row mp = ld_row(S.mp + r * 4);
     if (EUL) {
+      // finish what frees registers first (a, rp, ttb, ph, cq die here): omega_p, the T tendency without T_vadv,
+      // phi and Ephi
+      {
+        Row om = ld_tile(S.omp, sw1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          om.x[j] = fma(A.eta_ave_w, fma(-rp.x[j], cd[j], a.x[j]), om.x[j]);
+          tta.x[j] = fma(-ttb.x[j], cd[j], tta.x[j]);
+        }
+        st_tile(S.omp, sw1, om);
+      }
+      kep = ld_tile(S.pec, sw1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ph.x[j] += cq[j];
+        kep.x[j] += ph.x[j];
+      }
+      st_tile(S.pec, sw1, ph);
       // column total S of div(v dp) and the vertical mass flux at this level's two interfaces
       // (F/routine_extracted.F90:233-254): eta(k+1) = hybi(k+1)*S - sum_{l<=k} divdp_l, 0 at the top and bottom
       double S4[4] = {0, 0, 0, 0};
@@ -742,11 +762,14 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       }
       // preq_vertadv (LV/CaarFunctor.hpp:504-547): fac+ = eta(k+1)/(2 dp), fac- = eta(k)/(2 dp); the one-sided
       // forms at the top and bottom follow from eta = 0 there
+      {
+        const Row dpk = ld_row(A.dp3d + on0);  // re-read (L1/L2 hit) rather than 4 doubles live through the scans
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double hr = 0.5 * fast_rcp(dp.x[j]);
-        ehi.x[j] *= hr;
-        elo.x[j] *= hr;
+        for (int j = 0; j < 4; ++j) {
+          const double hr = 0.5 * fast_rcp(dpk.x[j]);
+          ehi.x[j] *= hr;
+          elo.x[j] *= hr;
+        }
       }
       // neighbouring levels come from the shared-memory tiles; only the first / last level of a split column
       // (CL = 2) reads its neighbour, which lives in the peer CTA, from global memory
@@ -779,6 +802,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
           if (kl > 0) ld_tile2(S.vn, (uint32_t)(tr - 2) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((tr - 2) & 7)) << 4), ud, vd);
           else ld_row2(A.v + (on0 - PTS) * 2, ud, vd);
         }
+        vt2 = ld_tile(S.Qd, sw1);  // parked there since the first half of the kernel
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // vtens = -v_vadv + ... (F:325-331)
           vt1.x[j] -= fma(ehi.x[j], uu.x[j] - uk.x[j], elo.x[j] * (uk.x[j] - ud.x[j]));
@@ -786,25 +810,32 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
         }
       }
     }
-    {  // derived_omega_p += eta_ave_w*omega (PO:173); T(np1) = spheremp*(T(nm1) + dt2*ttens) (PO:253)
-      Row om = ld_tile(S.omp, sw1), Tn = ld_tile(S.Tm1, sw1);
+    if constexpr (EUL) {  // T(np1) = spheremp*(T(nm1) + dt2*ttens); omega_p, phi and Ephi were done above
+      Row Tn = ld_tile(S.Tm1, sw1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Tn.x[j] = mp.x[j] * fma(A.dt2, tta.x[j], Tn.x[j]);
+      st_tile(S.Tm1, sw1, Tn);
+    } else {
+      {  // derived_omega_p += eta_ave_w*omega (PO:173); T(np1) = spheremp*(T(nm1) + dt2*ttens) (PO:253)
+        Row om = ld_tile(S.omp, sw1), Tn = ld_tile(S.Tm1, sw1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double omega = fma(-rp.x[j], cd[j], a.x[j]);
+          om.x[j] = fma(A.eta_ave_w, omega, om.x[j]);
+          const double tt = fma(-ttb.x[j], cd[j], tta.x[j]);
+          Tn.x[j] = mp.x[j] * fma(A.dt2, tt, Tn.x[j]);
+        }
+        st_tile(S.omp, sw1, om);
+        st_tile(S.Tm1, sw1, Tn);
+      }
+      // phi (PO:294,303,309) in place over pecnd; Ephi = 0.5|v|^2 + phi + pecnd (PO:196)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double omega = fma(-rp.x[j], cd[j], a.x[j]);
-        om.x[j] = fma(A.eta_ave_w, omega, om.x[j]);
-        const double tt = fma(-ttb.x[j], cd[j], tta.x[j]);
-        Tn.x[j] = mp.x[j] * fma(A.dt2, tt, Tn.x[j]);
+        ph.x[j] += cq[j];
+        kep.x[j] += ph.x[j];
       }
-      st_tile(S.omp, sw1, om);
-      st_tile(S.Tm1, sw1, Tn);
+      st_tile(S.pec, sw1, ph);
     }
-    // phi (PO:294,303,309) in place over pecnd; Ephi = 0.5|v|^2 + phi + pecnd (PO:196)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      ph.x[j] += cq[j];
-      kep.x[j] += ph.x[j];
-    }
-    st_tile(S.pec, sw1, ph);
     {  // v(np1) = spheremp*(v(nm1) + dt2*vtens) (PO:251-252), in place over v(nm1)
       Row g0, g1;
       gradient(kep, S.dinv + r * GS, cx, A.dvv, g0, g1);
