@@ -154,6 +154,30 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
+def randomize_like_reference_bench(td, seed):
+    """Fields U(1/64, 1), D random with |det D| >= 1/64, Dinv = D^-1, metdet = |det D| — the recipe of the reference's
+    Kokkos bench (level_vectorized_ppscan/Elements.cpp:101-152), which seeds from std::random_device; here a fixed
+    seed (numpy PCG64, so the values are not those of any mt19937_64 run). dp3d stays positive by construction."""
+    rng = np.random.default_rng(seed)
+    A = td.arrays
+    for n, a in A.items():
+        if n in ("elem_D", "elem_Dinv", "elem_metdet", "elem_rmetdet"):
+            continue
+        a[...] = rng.uniform(1.0 / 64, 1.0, size=a.shape)
+    D = rng.uniform(1.0 / 64, 1.0, size=A["elem_D"].shape)
+    det = D[..., 0, 0] * D[..., 1, 1] - D[..., 0, 1] * D[..., 1, 0]
+    bad = np.abs(det) < 1.0 / 64
+    D[bad] = np.array([[1.0, 0.25], [0.125, 0.75]])
+    det = D[..., 0, 0] * D[..., 1, 1] - D[..., 0, 1] * D[..., 1, 0]
+    A["elem_D"][...] = D
+    A["elem_Dinv"][..., 0, 0] = D[..., 1, 1] / det
+    A["elem_Dinv"][..., 0, 1] = -D[..., 0, 1] / det
+    A["elem_Dinv"][..., 1, 0] = -D[..., 1, 0] / det
+    A["elem_Dinv"][..., 1, 1] = D[..., 0, 0] / det
+    A["elem_metdet"][...] = np.abs(det)
+    A["elem_rmetdet"][...] = 1.0 / np.abs(det)
+
+
 def cpu_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -228,6 +252,9 @@ def main():
                     help="weak: --nelem elements per GPU (default); strong: --nelem elements in total, cut into "
                          "contiguous blocks per rank (BASELINE configs[3]/[4] strong-scaling variants)")
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--data", default="closed-form", choices=["closed-form", "random"],
+                    help="closed-form: the reference's init (PO/data_structures.cpp:38-92); random: U(1/64,1) fields and a "
+                         "random D with |det| >= 1/64, Dinv = D^-1 (the recipe of LV/Elements.cpp:101-152, fixed seed)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-chunk", type=int, default=0, help="elements per pipeline chunk (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -298,6 +325,8 @@ def main():
         def alloc(shape):  # noqa: F811
             return np.zeros(shape, dtype=np.float64)
     td = TestData(E, L, alloc=alloc).init_data(elem_offset=elem_offset)
+    if args.data == "random":
+        randomize_like_reference_bench(td, seed=20261018 + rank)
     h = tb.Caar(E, L, device=local_rank)
     h.set_params(td.consts, td.dvv, td.ps0, td.hyai)
     h.set_control(*[int(x) for x in td.ctl], dt2=td.dt2)
@@ -376,7 +405,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference closed-form init)",
+            "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (reference closed-form init)" if args.data == "closed-form" else
+                    "synthetic (random U(1/64,1) fields, random D with |det|>=1/64: LV/Elements.cpp:101-152 recipe)",
             "config": {"workload": f"{WORKLOADS.get((E_total // (world if args.scaling == 'weak' else 1), L), 'cubed sphere')}: "
                                    f"{E} elements per GPU ({E_total} in total), np=4, nlev={L}, FP64, "
                                    f"n0/np1/nm1 distinct, qn0=0",
