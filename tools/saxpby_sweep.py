@@ -56,6 +56,22 @@ def main():
     big = [r["GBps"] for r in rows if r["footprint_bytes"] >= (1 << 30)]
     doc = {"kernel": "saxpby_kernel (x=a*x+b*y, FP64)", "bytes_per_element": 24,
            "hbm_plateau_GBps": max(big) if big else None, "gpu": torch.cuda.get_device_name(0), "rows": rows}
+    # CPU leg: the reference's own saxpby (saxpby_test/cxx/common.cpp, OpenMP) on the host cores,
+    # at the reference's default size I1=1000 (262 MB per array), 100 sweeps like saxpby_test/cxx/main.cpp:39-41
+    try:
+        import numpy as np
+        from oracle import harness
+        ref = harness.RefSaxpby()
+        i1 = 1000
+        n = i1 * 128 * 256
+        xh, yh = np.ones(n), np.full(n, 1e-3)
+        ref.run(0.5, 5.0, xh, yh, sweeps=2)
+        sec = ref.run(0.5, 5.0, xh, yh, sweeps=100)
+        doc["cpu_reference"] = {"GBps": 24.0 * n * 100 / sec / 1e9, "I1": i1, "sweeps": 100,
+                                "threads": len(os.sched_getaffinity(0)), "kind": "reference (OpenMP)"}
+        print(f"CPU reference saxpby: {doc['cpu_reference']['GBps']:.1f} GB/s on {doc['cpu_reference']['threads']} threads")
+    except Exception as exc:  # the CPU leg is optional (oracle/_ref may be absent)
+        doc["cpu_reference"] = {"unavailable": str(exc)}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(doc, open(args.out, "w"), indent=1)
 
