@@ -416,3 +416,28 @@ def test_eulerian_through_the_host_call(mode):
     run_gpu_eulerian(got, hybi, 1, mode, host_path=6)
     check(got, want, exact=(mode == tb.MODE_STRICT))
     assert not np.array_equal(got.arrays["elem_derived_eta_dot_dpdn"], harness.randomize(orc.init(21), seed=8).arrays["elem_derived_eta_dot_dpdn"])
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+def test_empty_and_single_element_ranges(mode):
+    """Edge cases of the element range: [k,k) is a no-op on every entry point, a one-element range and a
+    one-element handle work (the cluster launch has no minimum grid)."""
+    orc = oracle_for(72)
+    base = harness.randomize(harness.PortOracle().init(5), seed=2)
+    got = base.copy()
+    got.ctl[0:2] = (3, 3)
+    run_gpu(got, 2, mode)
+    run_gpu_host(got, 1, mode, 0)
+    for n in harness.FIELD_NAMES:
+        assert np.array_equal(got.arrays[n], base.arrays[n]), n
+    want = base.copy()
+    want.ctl[0:2] = (4, 5)
+    got = want.copy()
+    orc.run(want)
+    run_gpu(got, 1, mode)
+    check(got, want, exact=(mode == tb.MODE_STRICT))
+    one = harness.randomize(harness.PortOracle().init(1), seed=4)
+    got1 = one.copy()
+    orc.run(one)
+    run_gpu(got1, 1, mode)
+    check(got1, one, exact=(mode == tb.MODE_STRICT))
