@@ -57,3 +57,17 @@ def test_driver_cli_errors():
     assert subprocess.run([exe, "--tinman-num-elems=abc"], capture_output=True).returncode == 1
     assert subprocess.run([exe, "--tinman-dump-res=maybe"], capture_output=True).returncode == 1
     assert subprocess.run([exe, "--tinman-help"], capture_output=True).returncode == 0
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_hommexx_style_f90_pointer_interface(mode, golden_dir):
+    """host/hommexx_shim.hpp (Control::init, Derivative::init, Elements::init_2d / pull_from_f90_pointers /
+    push_to_f90_pointers — the names and argument order of level_vectorized_ppscan/) driven by a C++ program that
+    hands over Fortran-order arrays: the norms are the reference driver's."""
+    exe = os.path.join(HOST, "hommexx_shim_test")
+    want = _vals(open(os.path.join(golden_dir, "pointers_only_stdout.txt")).read())[3:]     # norms after the run
+    out = subprocess.run([exe, "10", "1", mode], capture_output=True, text=True, check=True).stdout
+    got = _vals(out)[:3]
+    assert np.max(np.abs(got - want) / want) < 1e-13
+    m = re.search(r"= ([0-9.eE+-]+) == Fortran T\(2,3,1,np1\) = ([0-9.eE+-]+)", out)
+    assert m and m.group(1) == m.group(2)
