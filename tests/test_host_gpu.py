@@ -71,3 +71,14 @@ def test_hommexx_style_f90_pointer_interface(mode, golden_dir):
     assert np.max(np.abs(got - want) / want) < 1e-13
     m = re.search(r"= ([0-9.eE+-]+) == Fortran T\(2,3,1,np1\) = ([0-9.eE+-]+)", out)
     assert m and m.group(1) == m.group(2)
+
+
+def test_saxpby_driver_matches_reference_protocol():
+    """host/saxpby_driver: the reference's saxpby_test driver protocol (I1 x 128 x 256 doubles, 100 sweeps of
+    x = 3x + 5y, 'Init:' / 'saxpby:' timer lines) on HBM-resident arrays, values checked on the host."""
+    exe = os.path.join(HOST, "saxpby_driver")
+    p = subprocess.run([exe, "8", "--check"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    lines = p.stdout.splitlines()
+    assert lines[0].split() == ["8", "128", "256"]
+    assert lines[1].startswith("Init: ") and lines[2].startswith("saxpby: ") and "check: ok" in p.stdout
