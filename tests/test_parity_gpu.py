@@ -128,9 +128,10 @@ def test_element_range_partition(mode):
         assert np.array_equal(got.arrays[n][8:], base.arrays[n][8:])
 
 
-@pytest.mark.parametrize("nlev", [8, 16, 24, 64, 100])
+@pytest.mark.parametrize("nlev", [8, 16, 24, 40, 64, 80, 96, 100, 112, 120])
 def test_other_level_counts(nlev):
-    """nlev without a fused-kernel instance falls back to the generic strict kernel — still on the GPU."""
+    """Multiples of 8 have a fused instance (one CTA or a cluster per element, csrc/caar_fused_more.cu); any other
+    nlev falls back to the generic reference-order kernel — still on the GPU."""
     orc = harness.PortOracle()
     want = harness.randomize(orc.init(5, nlev), seed=nlev)
     gs, gf = want.copy(), want.copy()
@@ -388,7 +389,7 @@ def run_gpu_eulerian(state, hybi, ncalls, mode, host_path=None):
 
 
 @pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
-@pytest.mark.parametrize("nlev", [72, 128, 24])
+@pytest.mark.parametrize("nlev", [72, 128, 24, 30, 96])
 @pytest.mark.parametrize("qn0,tls", [(0, (0, 1, 2)), (-1, (0, 0, 0))])
 def test_eulerian_vertical_coordinate(mode, nlev, qn0, tls):
     """rsplit == 0 (eta_dot_dpdn from the divergence sum and hybi, preq_vertadv, vertical flux

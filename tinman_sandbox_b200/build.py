@@ -18,7 +18,7 @@ def build(force=False, verbose=False):
     csrc = os.path.join(HERE, "csrc")
     if force:
         subprocess.check_call(["make", "-C", csrc, "clean"], stdout=out)
-    subprocess.check_call(["make", "-C", csrc], stdout=out)
+    subprocess.check_call(["make", "-j4", "-C", csrc], stdout=out)
     host = os.path.join(HERE, "host")
     if os.path.exists(os.path.join(host, "Makefile")):
         if force:

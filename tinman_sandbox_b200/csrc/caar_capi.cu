@@ -208,7 +208,7 @@ int caar_create(caar_handle* out, const caar_dims* dims, int device) {
   }
   h->stream = h->own_stream;
   h->rsplit = 1;
-  if (dims->nlev == 72 || dims->nlev == 128) {
+  if (caar::fused_supports(dims->nlev)) {
     h->tma = new (std::nothrow) caar::TmaMaps();
     char msg[256] = "host allocation failed";
     if (!h->tma || caar::build_tma_maps(h->tma, make_args(h, nullptr), msg, sizeof msg)) {
@@ -531,7 +531,7 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
     caar::KernelArgs za = make_args(h, ctl, mapped);
     za.tma = nullptr;
     za.pf_dist = -1;  // no L2 prefetch of host memory
-    if (d.nlev == 72 || d.nlev == 128) {
+    if (caar::fused_supports(d.nlev)) {
       if (!h->tma_host || std::memcmp(h->tma_host_key, mapped, sizeof mapped) != 0) {
         if (!h->tma_host) h->tma_host = new (std::nothrow) caar::TmaMaps();
         char msg[256] = "host allocation failed";

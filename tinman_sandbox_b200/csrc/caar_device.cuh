@@ -65,8 +65,7 @@ cudaError_t launch_strict(const KernelArgs& a, cudaStream_t s);
 cudaError_t launch_fused(const KernelArgs& a, cudaStream_t s);
 bool fused_supports(int nlev);
 bool fused_supports_eulerian(int nlev);  // rsplit == 0 on the fused path
-cudaError_t launch_fused_ldg(const KernelArgs& a, cudaStream_t s);
-bool fused_ldg_supports(int nlev);
+cudaError_t launch_fused_more(const KernelArgs& a, cudaStream_t s);  // level counts other than 72 / 128
 size_t strict_smem_bytes(int nlev);
 
 cudaError_t launch_norms(const KernelArgs& a, int tl, int nets, int nete, double* partial /*[nelem][3]*/,
