@@ -89,7 +89,8 @@ enum {
 /* Compile-time dimensions of the reference (config.h.in:1-7), made run-time here. */
 typedef struct caar_dims {
   int nelem;   /* number of elements held by this handle (a rank's slice)      */
-  int nlev;    /* PLEV: 72 or 128 have tuned kernels; others use the generic kernel */
+  int nlev;    /* PLEV: fused kernels for 72 and 128 (tuned) and every other multiple of 8 up to 64, 80, 96, 112,
+                  120; any other value >= 2 runs on the generic reference-order kernel */
   int np;      /* must be 4 */
   int qsize_d; /* QSIZE_D (1 in the reference) */
   int ntl;     /* NUM_TIME_LEVELS (3) */
