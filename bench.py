@@ -205,7 +205,7 @@ def cpu_reference_rate(nlev, target_s=15.0, threads=None, calls=None):
     s = orc.init(E, nlev)
     t1 = orc.run(s, 1, threads)                       # also warms the pages
     if calls is None:
-        calls = max(1, min(200, int(target_s / max(t1, 1e-6))))
+        calls = max(1, min(5000, int(target_s / max(t1, 1e-6))))
     t = orc.run(s, calls, threads)
     rate = E * nlev * calls / t
     sample = (f"{E} elements (256 per thread) x {calls} calls, nlev={nlev}, closed-form init, "
@@ -403,7 +403,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_per_launch(E, L), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8000": achieved / 8000.0,
-                "kernel": "caar_fused_kernel" if mode == tb.MODE_FAST else "caar_strict_kernel"}
+                "kernel": "caar_fused_kernel" if mode == tb.MODE_FAST else "caar_strict_kernel",
+                "note": "the measured peak is a 50/50 read/write copy; this kernel's traffic is 62 % reads, and the "
+                        "library's own saxpby (67 % reads) streams 6.6-6.8 TB/s on the same GPUs (profiles/README.md)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
