@@ -144,10 +144,6 @@ __device__ __forceinline__ void ld_row2(const double* p, Row& u, Row& w) {  // i
     w.x[j] = a.y;
   }
 }
-__device__ __forceinline__ void st_row2(double* p, const Row& u, const Row& w) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(p + 2 * j) = make_double2(u.x[j], w.x[j]);
-}
 // Tiles written by TMA with SWIZZLE_128B: inside every 1024-byte block the 16-byte chunk index (address bits
 // 4-6) is XORed with the 128-byte row index (bits 7-9). `sw` is this thread's byte offset of its first chunk;
 // its other chunks are sw ^ 16, sw ^ 32, sw ^ 48. The 8 lanes of a quarter-warp hit 8 different chunk columns:
