@@ -255,9 +255,9 @@ def test_streamed_host_call(mode, chunk, qn0, tls):
 
 
 @pytest.mark.parametrize("chunk", [5, tb.HOST_ZERO_COPY])
-@pytest.mark.parametrize("nlev", [128, 24])
+@pytest.mark.parametrize("nlev", [128, 24, 96, 30])
 def test_streamed_host_call_other_nlev(nlev, chunk):
-    """nlev=128 (TMA kernel) and nlev=24 (generic kernel) through both host paths; the staged path also takes
+    """nlev=128 / 96 (cluster instances), 24 (one CTA per element) and 30 (reference-order kernel) through both host paths; the staged path also takes
     numpy (pageable) host memory."""
     orc = oracle_for(nlev)
     want = harness.randomize(harness.PortOracle().init(13, nlev), seed=3)
@@ -383,8 +383,14 @@ def run_gpu_eulerian(state, hybi, ncalls, mode, host_path=None):
         h.compute_and_apply_rhs(ncalls, mode)
         h.download(state.arrays, names=None)
     else:
-        for _ in range(ncalls):
-            h.compute_and_apply_rhs_host(state.arrays, mode, host_path)
+        if host_path == tb.HOST_ZERO_COPY:
+            tb.host_register(state.arrays)
+        try:
+            for _ in range(ncalls):
+                h.compute_and_apply_rhs_host(state.arrays, mode, host_path)
+        finally:
+            if host_path == tb.HOST_ZERO_COPY:
+                tb.host_unregister(state.arrays)
     h.close()
 
 
@@ -407,14 +413,16 @@ def test_eulerian_vertical_coordinate(mode, nlev, qn0, tls):
 
 
 @pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
-def test_eulerian_through_the_host_call(mode):
-    """The host-array pipeline moves eta_dot_dpdn both ways on the Eulerian branch (it is really updated)."""
+@pytest.mark.parametrize("host_path", [6, tb.HOST_ZERO_COPY])
+def test_eulerian_through_the_host_call(mode, host_path):
+    """The host-array pipeline moves eta_dot_dpdn both ways on the Eulerian branch (it is really updated); on the
+    zero-copy path the kernel read-modify-writes it in the caller's mapped memory."""
     orc = harness.PortOracle()
     want = harness.randomize(orc.init(21), seed=8)
     hybi = np.linspace(0.0, 1.0, 73)
     got = want.copy()
     orc.run_eulerian(want, hybi, 1, 2)
-    run_gpu_eulerian(got, hybi, 1, mode, host_path=6)
+    run_gpu_eulerian(got, hybi, 1, mode, host_path=host_path)
     check(got, want, exact=(mode == tb.MODE_STRICT))
     assert not np.array_equal(got.arrays["elem_derived_eta_dot_dpdn"], harness.randomize(orc.init(21), seed=8).arrays["elem_derived_eta_dot_dpdn"])
 
