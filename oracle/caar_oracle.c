@@ -137,6 +137,75 @@ static void vort_sphere(const double* v, const double* dvv, const double* d, con
     }
 }
 
+/* divergence_sphere_wk, the weak (integrated-by-parts) divergence behind hyperviscosity:
+ * level_vectorized_ppscan/SphereOperators.hpp:493-535 (= tiled_vectorized_ppscan/SphereOperators.hpp:421-455), in the
+ * pointers_only index convention (HOMMEXX view (igp,jgp) == pointers_only [jgp][igp], tensors (x,y) == [.][.][y][x]):
+ *   vtemp[i][j][c] = Dinv[i][j][c][0]*v0 + Dinv[i][j][c][1]*v1
+ *   div[m][n] = - sum_j ( spheremp[j][n]*vtemp[j][n][0]*Dvv[m][j] + spheremp[m][j]*vtemp[m][j][1]*Dvv[n][j] ) * rrearth
+ * accumulated from 0 by repeated `dd -= term` in j order, every product left to right, as the reference writes it
+ * (its accumulator `Scalar dd;` is zero-initialised by the vendored Vector's default constructor,
+ * level_vectorized_ppscan/vector/KokkosKernels_Vector_SIMD.hpp:32-37). Pinned to the reference's own code run under
+ * oracle/kokkos_stub (tests/test_oracle.py). */
+static void div_sphere_wk(const double* v, const double* dvv, const double* dinv, const double* spheremp,
+                          double rrearth, double* div) {
+  double t[NP][NP][2];
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      const double* di = dinv + (i * NP + j) * 4;
+      const double v0 = v[(i * NP + j) * 2], v1 = v[(i * NP + j) * 2 + 1];
+      t[i][j][0] = di[0] * v0 + di[1] * v1;
+      t[i][j][1] = di[2] * v0 + di[3] * v1;
+    }
+  for (int m = 0; m < NP; ++m)
+    for (int n = 0; n < NP; ++n) {
+      double dd = 0.0;
+      for (int j = 0; j < NP; ++j)
+        dd -= (spheremp[j * NP + n] * t[j][n][0] * dvv[m * NP + j] + spheremp[m * NP + j] * t[m][j][1] * dvv[n * NP + j]) *
+              rrearth;
+      div[m * NP + n] = dd;
+    }
+}
+
+/* laplace_simple / laplace_tensor / laplace_tensor_replace (level_vectorized_ppscan/SphereOperators.hpp:537-636):
+ * gradient_sphere, optionally g <- tensorVisc . g (gv[c] = tv[i][j][c][0]*g0 + tv[i][j][c][1]*g1), then
+ * divergence_sphere_wk. tensorvisc == NULL selects laplace_simple. */
+static void laplace_wk(const double* s, const double* dvv, const double* dinv, const double* spheremp,
+                       const double* tensorvisc, double rrearth, double* lap) {
+  double g[PTS * 2];
+  grad_sphere(s, dvv, dinv, rrearth, g);
+  if (tensorvisc)
+    for (int q = 0; q < PTS; ++q) {
+      const double* tv = tensorvisc + q * 4;
+      const double g0 = g[q * 2], g1 = g[q * 2 + 1];
+      g[q * 2] = tv[0] * g0 + tv[1] * g1;
+      g[q * 2 + 1] = tv[2] * g0 + tv[3] * g1;
+    }
+  div_sphere_wk(g, dvv, dinv, spheremp, rrearth, lap);
+}
+
+/* preq_vertadv, the vertical advection of T and v (CCM2 3.b.1): level_vectorized_ppscan/CaarFunctor.hpp:504-547.
+ * T, rpdel, T_vadv [L][16]; v, v_vadv [L][16][2]; eta_dp_deta [L+1][16]. Pinned to the reference's own code. */
+static void preq_vertadv(int L, const double* T, const double* v, const double* eta, const double* rpdel,
+                         double* T_vadv, double* v_vadv) {
+  for (int k = 0; k < L; ++k)
+    for (int q = 0; q < PTS; ++q) {
+      const size_t n = (size_t)k * PTS + q;
+      const double facp = 0.5 * rpdel[n] * eta[n + PTS];
+      const double facm = 0.5 * rpdel[n] * eta[n];
+      if (k == 0) {
+        T_vadv[n] = facp * (T[n + PTS] - T[n]);
+        for (int h = 0; h < 2; ++h) v_vadv[n * 2 + h] = facp * (v[(n + PTS) * 2 + h] - v[n * 2 + h]);
+      } else if (k < L - 1) {
+        T_vadv[n] = facp * (T[n + PTS] - T[n]) + facm * (T[n] - T[n - PTS]);
+        for (int h = 0; h < 2; ++h)
+          v_vadv[n * 2 + h] = facp * (v[(n + PTS) * 2 + h] - v[n * 2 + h]) + facm * (v[n * 2 + h] - v[(n - PTS) * 2 + h]);
+      } else {
+        T_vadv[n] = facm * (T[n] - T[n - PTS]);
+        for (int h = 0; h < 2; ++h) v_vadv[n * 2 + h] = facm * (v[n * 2 + h] - v[(n - PTS) * 2 + h]);
+      }
+    }
+}
+
 /* ---- vertical integrals -------------------------------------------------------------------- */
 
 /* reverse (bottom-up) sum; phii is an [L][16] scratch. PO/compute_and_apply_rhs.cpp:287-311 */
@@ -186,17 +255,19 @@ static void omega_ps(int L, const double* p, const double* vgrad_p, const double
 typedef struct {
   double *p, *grad_p, *vgrad_p, *vdp, *divdp, *vort, *T_v, *omega, *phii, *vt1, *vt2, *tt;
   double* eta; /* [L+1][16] interface values of eta_dot_dpdn (Eulerian branch) */
+  double *rpdel, *T_vadv, *v_vadv; /* Eulerian branch: 1/dp and the output of preq_vertadv */
 } scratch_t;
 
 static int scratch_alloc(scratch_t* w, int L) {
   const size_t n = (size_t)L * PTS;
-  double* base = (double*)calloc(n * 14 + n + PTS, sizeof(double));
+  double* base = (double*)calloc(n * 14 + n + PTS + 4 * n, sizeof(double));
   if (!base) return -1;
   w->p = base;            w->grad_p = base + n;      w->vgrad_p = base + 3 * n;
   w->vdp = base + 4 * n;  w->divdp = base + 6 * n;   w->vort = base + 7 * n;
   w->T_v = base + 8 * n;  w->omega = base + 9 * n;   w->phii = base + 10 * n;
   w->vt1 = base + 11 * n; w->vt2 = base + 12 * n;    w->tt = base + 13 * n;
   w->eta = base + 14 * n;
+  w->rpdel = base + 15 * n + PTS; w->T_vadv = w->rpdel + n; w->v_vadv = w->T_vadv + n;
   return 0;
 }
 
@@ -292,6 +363,11 @@ static void rhs_element(const ctx_t* c, int ie, scratch_t* w) {
     for (int q = 0; q < PTS; ++q) eta_dot[lf + q] += c->eta_ave_w * zero;
   }
 
+  if (c->rsplit == 0) { /* rpdel = 1/dp (fortran/routine_extracted.F90:120) */
+    for (size_t n = 0; n < lf; ++n) w->rpdel[n] = 1.0 / dp_n0[n];
+    preq_vertadv(L, T_n0, v_n0, w->eta, w->rpdel, w->T_vadv, w->v_vadv);
+  }
+
   /* G: tendencies (PO:187-234). v_vadv and T_vadv are identically zero in the reference. */
   for (int k = 0; k < L; ++k) {
     double Ephi[PTS], gT[PTS * 2], gE[PTS * 2], vgrad_T[PTS];
@@ -307,29 +383,11 @@ static void rhs_element(const ctx_t* c, int ie, scratch_t* w) {
     grad_sphere(Ephi, c->dvv, Dinv, c->rrearth, gE);
     const double* gp = w->grad_p + (size_t)k * PTS * 2;
     if (c->rsplit == 0) {
-      /* preq_vertadv, CCM2 (3.b.1): level_vectorized_ppscan/CaarFunctor.hpp:504-547 (rpdel = 1/dp,
-       * fortran/routine_extracted.F90:120), then the tendencies with the Fortran signs
-       * (fortran/routine_extracted.F90:325-334: ttens = -T_vadv - vgrad_T + kappa*T_v*omega_p) */
+      /* vertical advection from preq_vertadv (computed for the whole column before this loop), then the tendencies
+       * with the Fortran signs (fortran/routine_extracted.F90:325-334: ttens = -T_vadv - vgrad_T + kappa*T_v*omega_p) */
       for (int q = 0; q < PTS; ++q) {
         const size_t n = (size_t)k * PTS + q;
-        const double rdp = 1.0 / dp_n0[n];
-        const double facp = 0.5 * rdp * w->eta[(k + 1) * PTS + q];
-        const double facm = 0.5 * rdp * w->eta[k * PTS + q];
-        double T_vadv, v_vadv0, v_vadv1;
-        if (k == 0) {
-          T_vadv = facp * (T_n0[n + PTS] - T_n0[n]);
-          v_vadv0 = facp * (v_n0[(n + PTS) * 2] - v_n0[n * 2]);
-          v_vadv1 = facp * (v_n0[(n + PTS) * 2 + 1] - v_n0[n * 2 + 1]);
-        } else if (k < L - 1) {
-          T_vadv = facp * (T_n0[n + PTS] - T_n0[n]) + facm * (T_n0[n] - T_n0[n - PTS]);
-          v_vadv0 = facp * (v_n0[(n + PTS) * 2] - v_n0[n * 2]) + facm * (v_n0[n * 2] - v_n0[(n - PTS) * 2]);
-          v_vadv1 = facp * (v_n0[(n + PTS) * 2 + 1] - v_n0[n * 2 + 1]) +
-                    facm * (v_n0[n * 2 + 1] - v_n0[(n - PTS) * 2 + 1]);
-        } else {
-          T_vadv = facm * (T_n0[n] - T_n0[n - PTS]);
-          v_vadv0 = facm * (v_n0[n * 2] - v_n0[(n - PTS) * 2]);
-          v_vadv1 = facm * (v_n0[n * 2 + 1] - v_n0[(n - PTS) * 2 + 1]);
-        }
+        const double T_vadv = w->T_vadv[n], v_vadv0 = w->v_vadv[n * 2], v_vadv1 = w->v_vadv[n * 2 + 1];
         const double gpterm = w->T_v[n] / w->p[n];
         const double glnps1 = c->Rgas * gpterm * gp[q * 2];
         const double glnps2 = c->Rgas * gpterm * gp[q * 2 + 1];
@@ -519,6 +577,37 @@ void caar_oracle_euler_step(int nlev, int qsize_d, double* const* arrays, const 
   }
 }
 
+
+/* ---- the weak-form operators and preq_vertadv, exported for the tests and as the oracle of caar_sphere_wk ---- */
+void caar_oracle_preq_vertadv(int nlev, const double* T, const double* v, const double* eta_dp_deta, const double* rpdel,
+                              double* T_vadv, double* v_vadv) {
+  preq_vertadv(nlev, T, v, eta_dp_deta, rpdel, T_vadv, v_vadv);
+}
+
+/* op 0: divergence_sphere_wk of vin [E][L][4][4][2]; op 1: laplace_simple, op 2: laplace_tensor of sin [E][L][4][4]
+ * (tensorvisc [E][4][4][2][2]); out [E][L][4][4]; elements [nets,nete). Uses the Dinv / spheremp arrays of the table. */
+void caar_oracle_sphere_wk(int op, int nlev, double* const* arrays, const double* vin, const double* sin,
+                           const double* tensorvisc, double* out, int nets, int nete, const double* dvv16,
+                           double rrearth) {
+  for (int ie = nets; ie < nete; ++ie) {
+    const double* dinv = arrays[F_DINV] + (size_t)ie * PTS * 4;
+    const double* spheremp = arrays[F_SPHEREMP] + (size_t)ie * PTS;
+    for (int k = 0; k < nlev; ++k) {
+      const size_t n = ((size_t)ie * nlev + k) * PTS;
+      if (op == 0) div_sphere_wk(vin + n * 2, dvv16, dinv, spheremp, rrearth, out + n);
+      else laplace_wk(sin + n, dvv16, dinv, spheremp, op == 2 ? tensorvisc + (size_t)ie * PTS * 4 : NULL, rrearth, out + n);
+    }
+  }
+}
+
+/* one level of gradient_sphere / vorticity_sphere (PO/sphere_operators.cpp:9-48, 91-129), for the operator pins */
+void caar_oracle_gradient_sphere(const double* s, const double* dvv16, const double* dinv, double rrearth, double* ds) {
+  grad_sphere(s, dvv16, dinv, rrearth, ds);
+}
+void caar_oracle_vorticity_sphere(const double* v, const double* dvv16, const double* d, const double* rmetdet,
+                                  double rrearth, double* vort) {
+  vort_sphere(v, dvv16, d, rmetdet, rrearth, vort);
+}
 
 /* closed-form synthetic fields; 1-based index values as in the reference (PO/data_structures.cpp:38-92) */
 void caar_oracle_init(int E, int L, int Q, int ntl, double* const* a, int* ctl, double* dt2, double* k6,

@@ -44,6 +44,21 @@ void caar_oracle_euler_step(int nlev, int qsize_d, double* const* arrays, const 
                             int nets, int nete, int qn0, int qsize, double dt, const double* dvv16,
                             double rrearth);
 
+/* preq_vertadv (level_vectorized_ppscan/CaarFunctor.hpp:504-547): T, rpdel, T_vadv [L][4][4]; v, v_vadv [L][4][4][2];
+ * eta_dp_deta [L+1][4][4]. The Eulerian branch of caar_oracle_run_eulerian calls exactly this. */
+void caar_oracle_preq_vertadv(int nlev, const double* T, const double* v, const double* eta_dp_deta, const double* rpdel,
+                              double* T_vadv, double* v_vadv);
+
+/* weak-form operators behind hyperviscosity (level_vectorized_ppscan/SphereOperators.hpp:493-636) in the pointers_only
+ * conventions: op 0 divergence_sphere_wk (vin [E][L][4][4][2]), op 1 laplace_simple, op 2 laplace_tensor (sin
+ * [E][L][4][4], tensorvisc [E][4][4][2][2]); out [E][L][4][4] */
+void caar_oracle_sphere_wk(int op, int nlev, double* const* arrays, const double* vin, const double* sin,
+                           const double* tensorvisc, double* out, int nets, int nete, const double* dvv16,
+                           double rrearth);
+void caar_oracle_gradient_sphere(const double* s, const double* dvv16, const double* dinv, double rrearth, double* ds);
+void caar_oracle_vorticity_sphere(const double* v, const double* dvv16, const double* d, const double* rmetdet,
+                                  double rrearth, double* vort);
+
 /* x = a*x + b*y (saxpby_test/cxx/common.cpp:3-15), nthreads pthreads; returns wall seconds */
 double caar_oracle_saxpby(double a, double b, double* x, const double* y, size_t n, int sweeps,
                           int nthreads);

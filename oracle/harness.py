@@ -180,6 +180,40 @@ class PortOracle:
                                         int(s.ctl[1]), int(qn0), int(qsize), C.c_double(dt), _dp(s.dvv),
                                         C.c_double(s.consts[0]))
 
+    def preq_vertadv(self, T, v, eta_dp_deta, rpdel):
+        """T, rpdel (L,4,4); v (L,4,4,2); eta_dp_deta (L+1,4,4) -> (T_vadv, v_vadv)
+        (level_vectorized_ppscan/CaarFunctor.hpp:504-547)."""
+        L = T.shape[0]
+        Tv, vv = np.zeros((L, 4, 4)), np.zeros((L, 4, 4, 2))
+        c = np.ascontiguousarray
+        self.lib.caar_oracle_preq_vertadv(L, _dp(c(T)), _dp(c(v)), _dp(c(eta_dp_deta)), _dp(c(rpdel)), _dp(Tv), _dp(vv))
+        return Tv, vv
+
+    def sphere_wk(self, name, s: State, field, tensorvisc=None, nets=None, nete=None):
+        """divergence_sphere_wk (field (E,L,4,4,2)) / laplace_simple / laplace_tensor (field (E,L,4,4), tensorvisc
+        (E,4,4,2,2)) -> (E,L,4,4); level_vectorized_ppscan/SphereOperators.hpp:493-636."""
+        op = {"divergence_sphere_wk": 0, "laplace_simple": 1, "laplace_tensor": 2}[name]
+        out = np.zeros((s.nelem, s.nlev, 4, 4))
+        f = np.ascontiguousarray(field)
+        tv = np.ascontiguousarray(tensorvisc) if tensorvisc is not None else None
+        self.lib.caar_oracle_sphere_wk(op, s.nlev, s.ptr_table(), _dp(f) if op == 0 else None,
+                                       _dp(f) if op != 0 else None, _dp(tv) if tv is not None else None, _dp(out),
+                                       int(s.ctl[0]) if nets is None else nets, int(s.ctl[1]) if nete is None else nete,
+                                       _dp(s.dvv), C.c_double(s.consts[0]))
+        return out
+
+    def gradient_sphere(self, sc, s: State, ie):
+        out = np.zeros((4, 4, 2))
+        self.lib.caar_oracle_gradient_sphere(_dp(np.ascontiguousarray(sc)), _dp(s.dvv), _dp(s.arrays["elem_Dinv"][ie]),
+                                             C.c_double(s.consts[0]), _dp(out))
+        return out
+
+    def vorticity_sphere(self, v, s: State, ie):
+        out = np.zeros((4, 4))
+        self.lib.caar_oracle_vorticity_sphere(_dp(np.ascontiguousarray(v)), _dp(s.dvv), _dp(s.arrays["elem_D"][ie]),
+                                              _dp(s.arrays["elem_rmetdet"][ie]), C.c_double(s.consts[0]), _dp(out))
+        return out
+
     def saxpby(self, a, b, x, y, sweeps=1, nthreads=1) -> float:
         return self.lib.caar_oracle_saxpby(C.c_double(a), C.c_double(b), _dp(x), _dp(y), C.c_size_t(x.size),
                                            sweeps, nthreads)
@@ -238,6 +272,94 @@ class RefSaxpby:
         i1 = x.size // (128 * 256)
         assert i1 * 128 * 256 == x.size
         return self.lib.saxpby_ref_run(C.c_double(a), C.c_double(b), _dp(x), _dp(y), i1, sweeps)
+
+
+class HommexxOracle:
+    """The reference's HOMMEXX prototypes — level_vectorized_ppscan ("lv") / tiled_vectorized_ppscan ("tv") —
+    compiled unmodified against oracle/kokkos_stub (oracle/Makefile) into oracle/_ref/libhommexx_<variant>_L<nlev>.so.
+    Every method takes and returns arrays in the pointers_only conventions ([.][igp][jgp]([c]) per level) and
+    converts to the order the reference's own code reads: Fortran memory order, which is also the index order of the
+    HOMMEXX views (level_vectorized_ppscan/Elements.cpp:48-99,154-292)."""
+    kind = "reference (HOMMEXX prototype under a serial Kokkos stand-in)"
+    OPS = {"gradient_sphere": 0, "divergence_sphere": 1, "vorticity_sphere": 2, "divergence_sphere_wk": 3,
+           "laplace_simple": 4, "laplace_tensor": 5, "laplace_tensor_replace": 6, "divergence_sphere_update": 7}
+
+    def __init__(self, variant="lv", nlev=72):
+        path = os.path.join(REF_DIR, f"libhommexx_{variant}_L{nlev}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.variant, self.nlev = variant, self.lib.hx_nlev()
+        self.qsize_d = self.lib.hx_qsize_d()
+        assert self.nlev == nlev and self.lib.hx_variant() == (1 if variant == "tv" else 0)
+
+    @staticmethod
+    def available(variant="lv", nlev=72):
+        return os.path.exists(os.path.join(REF_DIR, f"libhommexx_{variant}_L{nlev}.so"))
+
+    def run(self, s: State, ncalls=1):
+        """compute_and_apply_rhs through Elements::pull_from_f90_pointers -> CaarFunctor -> push_to_f90_pointers.
+        Needs s.qsize_d == the library's QSIZE_D and the reference's physical constants (they are compile-time in
+        HOMMEXX: level_vectorized_ppscan/PhysicalConstants.hpp:11-18). ps0 is an `int` member there (Control.hpp:50)."""
+        assert s.nlev == self.nlev and s.qsize_d == self.qsize_d and s.ntl == 3
+        f = to_f90(s.arrays)
+        A = lambda n: _dp(f[n])
+        dvv_f90 = np.ascontiguousarray(s.dvv.T)
+        self.lib.hx_caar_f90(s.nelem, A("elem_D"), A("elem_Dinv"), A("elem_fcor"), A("elem_spheremp"), A("elem_metdet"),
+                             A("elem_state_phis"), A("elem_state_v"), A("elem_state_T"), A("elem_state_dp3d"),
+                             A("elem_derived_phi"), A("elem_derived_pecnd"), A("elem_derived_omega_p"),
+                             A("elem_derived_vn0"), A("elem_derived_eta_dot_dpdn"), A("elem_state_Qdp"),
+                             int(s.ctl[0]), int(s.ctl[1]), int(s.ctl[4]), int(s.ctl[2]), int(s.ctl[3]), int(s.ctl[5]),
+                             C.c_double(s.dt2), C.c_double(s.ps0), C.c_double(s.consts[1]), _dp(s.hyai), _dp(dvv_f90),
+                             int(ncalls))
+        back = from_f90(f)
+        for n in MUTATED:
+            s.arrays[n][...] = back[n]
+
+    def sphere_op(self, name, field, s: State, ie, tensorvisc=None, alpha=1.0, beta=0.0, out=None):
+        """One of OPS on every level of element ie. Scalars are (L,4,4), vectors (L,4,4,2) in pointers_only order;
+        tensorvisc (4,4,2,2) like elem_D. divergence_sphere_update: out = beta*out + alpha*div(field)."""
+        op = self.OPS[name]
+        L = self.nlev
+        A = s.arrays
+        t4 = lambda a: np.ascontiguousarray(a.transpose(3, 2, 1, 0))            # [i][j][a][b] -> [b][a][j][i]
+        t2 = lambda a: np.ascontiguousarray(a.T)
+        vec_in = op in (1, 2, 3, 7)
+        fin = np.ascontiguousarray(field.transpose(0, 3, 2, 1) if vec_in else field.transpose(0, 2, 1))
+        vec_out = op == 0
+        fout = np.zeros((L, 2, 4, 4) if vec_out else (L, 4, 4))
+        if op == 7:
+            fout[...] = out.transpose(0, 2, 1)
+        tv = t4(tensorvisc) if tensorvisc is not None else None
+        rc = self.lib.hx_sphere_op(op, _dp(t4(A["elem_D"][ie])), _dp(t4(A["elem_Dinv"][ie])), _dp(t2(A["elem_metdet"][ie])),
+                                   _dp(t2(A["elem_spheremp"][ie])), _dp(tv) if tv is not None else None,
+                                   _dp(t2(s.dvv)), _dp(fin), _dp(fout), C.c_double(alpha), C.c_double(beta))
+        assert rc == 0
+        return np.ascontiguousarray(fout.transpose(0, 3, 2, 1) if vec_out else fout.transpose(0, 2, 1))
+
+    def preq_vertadv(self, T, v, eta_dp_deta, rpdel):
+        """CaarFunctor::preq_vertadv: T, rpdel (L,4,4), v (L,4,4,2), eta_dp_deta (L+1,4,4) -> (T_vadv, v_vadv)."""
+        L = self.nlev
+        sw = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1))
+        Tv, vv = np.zeros((L, 4, 4)), np.zeros((L, 2, 4, 4))
+        self.lib.hx_preq_vertadv(_dp(sw(T)), _dp(np.ascontiguousarray(v.transpose(0, 3, 2, 1))), _dp(sw(eta_dp_deta)),
+                                 _dp(sw(rpdel)), _dp(Tv), _dp(vv))
+        return sw(Tv), np.ascontiguousarray(vv.transpose(0, 3, 2, 1))
+
+    def euler_step(self, s: State, vstar, qn0, qsize, dt):
+        """EulerStepFunctor::operator() (tiled_vectorized_ppscan/EulerStepFunctor.hpp:33-70) on every element ->
+        qtens (E, qsize_d, L, 4, 4). TV only (the LV copy of the functor does not compile, see ref_hommexx_capi.cpp)."""
+        assert self.variant == "tv" and s.qsize_d == self.qsize_d and s.nlev == self.nlev
+        E, L, Q = s.nelem, s.nlev, s.qsize_d
+        A = s.arrays
+        dinv = np.ascontiguousarray(A["elem_Dinv"].transpose(0, 4, 3, 2, 1))
+        met = np.ascontiguousarray(A["elem_metdet"].transpose(0, 2, 1))
+        vs = np.ascontiguousarray(vstar.transpose(0, 1, 4, 3, 2))
+        qdp = np.ascontiguousarray(A["elem_state_Qdp"].transpose(0, 2, 1, 3, 5, 4))
+        qt = np.zeros((E, Q, L, 4, 4))
+        self.lib.hx_euler_step(E, int(qsize), int(qn0), C.c_double(dt), _dp(dinv), _dp(met),
+                               _dp(np.ascontiguousarray(s.dvv.T)), _dp(vs), _dp(qdp), _dp(qt))
+        return np.ascontiguousarray(qt.transpose(0, 1, 2, 4, 3))
 
 
 def best_oracle(nlev=72):

@@ -23,12 +23,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_saxpby_sweep.json"))
     ap.add_argument("--max-gb", type=float, default=16.0)
+    ap.add_argument("--min-gb", type=float, default=0.0, help="first footprint of the sweep (0 = 1 MB)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the reference's OpenMP saxpby on the host")
     args = ap.parse_args()
     lib = tb.load_library()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream()
     rows = []
     total = 1 << 20  # bytes over both arrays
+    if args.min_gb > 0:
+        total = int(args.min_gb * (1 << 30))
     while total <= args.max_gb * (1 << 30):
         n = total // 16
         x = torch.ones(n, dtype=torch.float64, device=dev)
@@ -59,6 +63,8 @@ def main():
     # CPU leg: the reference's own saxpby (saxpby_test/cxx/common.cpp, OpenMP) on the host cores,
     # at the reference's default size I1=1000 (262 MB per array), 100 sweeps like saxpby_test/cxx/main.cpp:39-41
     try:
+        if args.no_cpu:
+            raise RuntimeError("skipped (--no-cpu)")
         import numpy as np
         from oracle import harness
         ref = harness.RefSaxpby()
