@@ -112,6 +112,11 @@ class ClockSampler:
                 pass
             self._stop.wait(self.period)
 
+    extended = False
+
+    def count_since_mark(self):
+        return len(self.samples) - getattr(self, "t_mark", 0)
+
     def mark(self):
         """Samples taken from here on belong to the timed region (plus the one in flight: the GPU has been under
         the same load for two steps when this is called, and an NVML query takes longer than a step)."""
@@ -127,7 +132,8 @@ class ClockSampler:
         sm = self.samples[getattr(self, "t_mark", 0):]
         if sm:
             out.update(sm_mhz=statistics.median(sm), reasons=sorted(self.reasons), samples=len(sm),
-                       power_w_max=max(self.power) if self.power else None)
+                       power_w_max=max(self.power) if self.power else None,
+                       window="timed region" + (" + the same kernel loop continued until 5 samples" if self.extended else ""))
         return out
 
 
@@ -214,40 +220,115 @@ def cpu_reference_rate(nlev, target_s=15.0, threads=None, calls=None):
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation (oracle/_ref: the unmodified pointers_only sources) on every host
+    thread, one unmodified routine per disjoint [nets,nete) range, over the FULL per-GPU workload of the b200 arm
+    (--nelem elements, default ne=120: 86400) — one call per step, like PO/main.cpp:113-121."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = cpu_threads()
     from oracle import harness
     orc = harness.best_oracle(args.nlev)
-    E = 512 * threads
-    calls = 2                                   # per step: amortises the per-step thread start-up
+    E = args.nelem
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 1 << 62
+    need = E * (186112.0 / 72 * args.nlev)
+    sampled = need > 0.6 * avail
+    if sampled:                                   # never on the pool's boxes; keeps the arm alive on a small host
+        E = max(threads, int(0.5 * avail / (186112.0 / 72 * args.nlev)) // threads * threads)
     s = orc.init(E, args.nlev)
     for _ in range(max(1, args.warmup)):
-        orc.run(s, calls, threads)
-    # each step = `calls` passes over the bounded sample; the whole run ends within a few minutes
+        orc.run(s, 1, threads)
     steps = args.steps
     t0 = time.perf_counter()
     total = 0.0
     for _ in range(steps):
-        total += orc.run(s, calls, threads)
+        total += orc.run(s, 1, threads)
     wall = time.perf_counter() - t0
-    rate = E * args.nlev * steps * calls / total
-    sample = (f"{E} elements (512 per thread) x {calls} calls per step, nlev={args.nlev}, closed-form init, "
-              f"{threads} threads on disjoint [nets,nete) ranges; the rate is per unit, so it stands for the "
-              f"{args.nelem}-element workload")
+    rate = E * args.nlev * steps / total
+    sample = (f"{E} elements x 1 call per step, nlev={args.nlev}, closed-form init, {threads} threads on disjoint "
+              f"[nets,nete) ranges" + ("; SUB-SAMPLED: the host cannot hold the full arrays" if sampled else
+                                       "; the full per-GPU workload of the b200 arm"))
+    if args.gpus > 1:
+        sample += (f"; the b200 arm at {args.gpus} GPUs holds {args.gpus} x {args.nelem} elements — the CPU rate is "
+                   f"per unit of work and does not depend on the element count")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference closed-form init)",
-        "config": {"workload": f"ne=120 cubed sphere: {args.nelem} elements per GPU, np=4, nlev={args.nlev}, FP64",
-                   "sampled": True},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": orc.kind, "sample": sample},
+        "config": {"workload": f"{WORKLOADS.get((args.nelem, args.nlev), 'cubed sphere')}: {args.nelem} elements per GPU, "
+                               f"np=4, nlev={args.nlev}, FP64, n0/np1/nm1 distinct, qn0=0",
+                   "elements_per_gpu": args.nelem, "nlev": args.nlev, "sampled": sampled, "elements_timed": E},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": orc.kind, "sample": sample,
+                         "cpu_model": cpu_model()},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ---- correctness attached to the speed records -------------------------------------------------------------------
+def sample_windows(E, seed):
+    """first / middle / last 16 elements + 16 random single elements of a rank's slice (fewer on tiny slices)"""
+    if E <= 64:
+        return [(0, E)]
+    rng = np.random.default_rng(seed)
+    mid = E // 2
+    w = [(0, 16), (mid - 8, mid + 8), (E - 16, E)]
+    w += [(int(e), int(e) + 1) for e in sorted(rng.choice(np.arange(16, E - 16), size=16, replace=False))]
+    return w
+
+
+def oracle_states(td, windows, nlev):
+    """harness.State copies of the window elements of td (the inputs as they are in the host arrays right now)"""
+    from oracle import harness
+    out = []
+    for (a, b) in windows:
+        st = harness.State(b - a, nlev)
+        st.arrays = {n: td.arrays[n][a:b].copy() for n in harness.FIELD_NAMES}
+        st.ctl = np.array([0, b - a] + [int(x) for x in td.ctl[2:6]], dtype=np.int32)
+        st.dt2, st.consts, st.dvv, st.ps0, st.hyai = td.dt2, td.consts.copy(), td.dvv.copy(), td.ps0, td.hyai.copy()
+        out.append(st)
+    return out
+
+
+def max_rel_err(got, want, names):
+    worst = 0.0
+    for n in names:
+        den = max(float(np.max(np.abs(want[n]))), 1e-300)
+        worst = max(worst, float(np.max(np.abs(got[n] - want[n]))) / den)
+    return worst
+
+
+def link_probe(dev, nbytes=1 << 28):
+    """What this GPU's host link does right now, in this process: host->device alone, device->host alone and both at
+    once (pinned 256 MiB buffers, two streams, best of 3) — the denominator of the end-to-end number."""
+    import torch
+    hin = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dout = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    res = {}
+    for name, do_in, do_out in (("h2d", True, False), ("d2h", False, True), ("duplex", True, True)):
+        best = 1e30
+        for _ in range(4):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            if do_in:
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            best = min(best, time.perf_counter() - t0)
+        res[name] = nbytes / best / 1e9
+    return res
 
 
 def main():
@@ -270,6 +351,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-target-s", type=float, default=15.0)
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check after the timed loops")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -356,7 +438,20 @@ def main():
     ms = h.timer_stop()
     barrier()
     launches = h.launch_count() - launches0
+    calls_done = args.warmup + 2 + args.steps
+    # A timed region shorter than ~5 NVML samples (small or strong-scaled slices): keep the SAME load running, outside
+    # the timed region, until the sampler has at least 5 — and say so; never print a clocks record with fewer.
+    if sampler and sampler.count_since_mark() < 5:
+        t_end = time.perf_counter() + 0.25
+        while sampler.count_since_mark() < 5 and time.perf_counter() < t_end:
+            h.compute_and_apply_rhs(args.steps, mode)
+            calls_done += args.steps
+        sampler.extended = True
+    barrier()
     clocks = sampler.stop() if sampler else None
+    if clocks and clocks.get("samples", 0) < 5:
+        clocks = {"sm_mhz": None, "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": [], "samples": clocks.get("samples", 0),
+                  "rejected": "fewer than 5 NVML samples under load"}
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -364,11 +459,42 @@ def main():
     ms_per_step = ms_max / args.steps
     value = E_total * L * args.steps / (ms_max * 1e-3)
 
-    # ---- norms: the only collective of the job (sum of squares all-reduced over NVLink, then sqrt)
-    ss = torch.from_numpy(h.sumsq(int(td.ctl[3]))).to(dev)
+    # ---- the collectives of the job, all AFTER the timed loop (NCCL over NVLink): squared norms of v, T, dp3d(np1)
+    # (print_results_2norm, PO/compute_and_apply_rhs.cpp:372-399), checksums of all seven mutated arrays and the two
+    # energy norms (caar_checksums), summed over ranks; the bit-pattern sums travel as 64-bit integers.
+    ss_local = h.sumsq(int(td.ctl[3]))
+    ss = torch.from_numpy(ss_local).to(dev)
+    cs = h.checksums(int(td.ctl[3]))
+    cs_f = torch.from_numpy(np.concatenate([cs["sum"], cs["sumsq"], cs["energy"]])).to(dev)
+    cs_b = torch.from_numpy(cs["bits"].view(np.int64).copy()).to(dev)
     if world > 1:
         dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cs_f, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cs_b, op=dist.ReduceOp.SUM)
     norms = torch.sqrt(ss).cpu().numpy().tolist()
+    cs_f = cs_f.cpu().numpy()
+    checksums = {"fields": list(tb.CHECKSUM_FIELDS), "sum": cs_f[:7].tolist(), "sumsq": cs_f[7:14].tolist(),
+                 "energy": {"kinetic": float(cs_f[14]), "internal": float(cs_f[15])},
+                 "bits": [format(int(x) & 0xFFFFFFFFFFFFFFFF, "016x") for x in cs_b.cpu().numpy()],
+                 "time_level": int(td.ctl[3]), "calls": calls_done}
+
+    # ---- parity of THIS run: a sample of this rank's slice against the CPU oracle after the same number of calls
+    parity = None
+    if not args.no_parity:
+        from oracle import harness
+        orc = harness.best_oracle(L)
+        wins = sample_windows(E, seed=1000 + rank)
+        states = oracle_states(td, wins, L)          # td still holds the inputs: nothing has written the host arrays
+        worst, nchk = 0.0, 0
+        for (a, b), st in zip(wins, states):
+            orc.run(st, calls_done, 1)
+            got = h.download_range(a, b, names=harness.MUTATED)
+            worst = max(worst, max_rel_err(got, st.arrays, harness.MUTATED))
+            nchk += b - a
+        parity = {"max_rel_err": worst, "elements_checked": nchk, "calls": calls_done, "oracle": orc.kind,
+                  "tolerance": 0.0 if mode == tb.MODE_STRICT else 1e-12,
+                  "what": "first/middle/last 16 + 16 random elements of every rank's slice, all 7 mutated arrays, "
+                          "max|a-b|/max|b| per field and window, max over ranks"}
 
     # ---- end to end through the reference-facing host semantics: host arrays in, host arrays out, per step
     e2e = None
@@ -376,6 +502,11 @@ def main():
         # every step: caar_run_host = copy-in of the slices the routine reads (pinned host arrays), the kernel,
         # copy-out of the slices it writes, pipelined over element chunks; results are in the host arrays
         h2d, d2h = h.host_traffic(mode)
+        e2e_states = None
+        if parity is not None:
+            e2e_wins = sample_windows(E, seed=2000 + rank)
+            e2e_states = oracle_states(td, e2e_wins, L)
+        link = link_probe(dev)
         h.compute_and_apply_rhs_host(td.arrays, mode, args.e2e_chunk)
         barrier()
         t0 = time.perf_counter()
@@ -387,13 +518,79 @@ def main():
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dt = float(t_e.item())
+        if e2e_states is not None:                   # the host arrays now hold 1 + e2e_steps calls: check them too
+            from oracle import harness
+            worst = 0.0
+            for (a, b), st in zip(e2e_wins, e2e_states):
+                orc.run(st, 1 + args.e2e_steps, 1)
+                worst = max(worst, max_rel_err({n: td.arrays[n][a:b] for n in harness.MUTATED}, st.arrays, harness.MUTATED))
+            parity["e2e_max_rel_err"] = worst
+            parity["e2e_calls"] = 1 + args.e2e_steps
+        lk = torch.tensor([link["h2d"], link["d2h"], link["duplex"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(lk, op=dist.ReduceOp.MIN)       # the slowest rank's link bounds the job
+        lk = lk.cpu().numpy()
+        h2d_rate = h2d * args.e2e_steps / dt / 1e9
         e2e = {"value": E_total * L * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "pcie_gbs": {"h2d": h2d * args.e2e_steps / dt / 1e9, "d2h": d2h * args.e2e_steps / dt / 1e9},
+               "pcie_gbs": {"h2d": h2d_rate, "d2h": d2h * args.e2e_steps / dt / 1e9},
+               "link": {"h2d_gbs": float(lk[0]), "d2h_gbs": float(lk[1]), "duplex_peak_gbs": float(lk[2]),
+                        "frac": h2d_rate / float(lk[2]), "bound": "host link (PCIe), host->device direction",
+                        "how": "256 MiB pinned copies in this process just before the timed e2e steps, one GPU per rank "
+                               "and all ranks at once: alone each way, then both ways at once (duplex, per direction); "
+                               "min over ranks; frac = achieved host->device GB/s of the e2e steps / duplex"},
                "how": "caar_run_host per step: host arrays in, host arrays out (%s), copy-in | kernel | "
                       "copy-out pipelined over element chunks; PCIe-bound" %
                       ("pinned" if pin_ok else "PAGEABLE: pinning would take >60% of host RAM")}
+    # ---- the protocol the reference driver's loop needs (PO/main.cpp:99-131): init -> [upload once] -> K calls ->
+    # [download once] -> norms. An extra number beside e2e (which pays the copies at EVERY call).
+    resident = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        h.upload(td.arrays)
+        t1 = time.perf_counter()
+        h.compute_and_apply_rhs(args.steps, mode)
+        t2 = time.perf_counter()
+        h.download(td.arrays)
+        t3 = time.perf_counter()
+        tt = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tt = tt.cpu().numpy()
+        resident = {"value": E_total * L * args.steps / float(tt[0]), "unit": UNIT, "steps": args.steps,
+                    "upload_s": float(tt[1]), "compute_s": float(tt[2]), "download_s": float(tt[3]),
+                    "how": "caar_upload of all 16 arrays once, %d caar_run calls, caar_download of the 7 mutated arrays "
+                           "once; wall clock, max over ranks" % args.steps}
+
+    # ---- the printed norms against the reference: one CPU call over this rank's whole slice (T, v, dp3d at np1 do not
+    # depend on the number of calls: the reference loop does not rotate time levels, PO/main.cpp:118)
+    if parity is not None:
+        from oracle import harness
+        os.sched_setaffinity(0, all_cpus)
+        st = harness.State(E, L)
+        st.arrays = td.arrays
+        st.ctl = np.array([0, E] + [int(x) for x in td.ctl[2:6]], dtype=np.int32)
+        st.dt2, st.consts, st.dvv, st.ps0, st.hyai = td.dt2, td.consts, td.dvv, td.ps0, td.hyai
+        orc.run(st, 1, max(1, cpu_threads() // max(1, world)))
+        want = np.array(orc.norms(st)) ** 2
+        nerr = torch.tensor([float(np.max(np.abs(ss_local - want) / want))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(nerr, op=dist.ReduceOp.MAX)
+        parity["norms_rel_err"] = float(nerr.item())
+        pm = torch.tensor([parity["max_rel_err"], parity.get("e2e_max_rel_err", 0.0)], dtype=torch.float64, device=dev)
+        pn = torch.tensor([parity["elements_checked"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pn, op=dist.ReduceOp.SUM)
+        parity["max_rel_err"] = float(pm[0].item())
+        if "e2e_max_rel_err" in parity:
+            parity["e2e_max_rel_err"] = float(pm[1].item())
+        parity["elements_checked"] = int(pn.item())
+        parity["ok"] = bool(parity["max_rel_err"] <= parity["tolerance"] and
+                            parity.get("e2e_max_rel_err", 0.0) <= parity["tolerance"] and
+                            parity["norms_rel_err"] <= 1e-13)
     h.close()
 
     # ---- roofline of the dominant (only) kernel of a step
@@ -431,7 +628,8 @@ def main():
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" %
                              (sum(a.nbytes for a in td.arrays.values()) / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "clocks": clocks, "norms_np1": norms,
+            "cpu_baseline": cpu_baseline, "clocks": clocks, "norms_np1": norms, "checksums": checksums,
+            "parity": parity, "resident_protocol": resident,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -89,8 +89,9 @@ enum {
 /* Compile-time dimensions of the reference (config.h.in:1-7), made run-time here. */
 typedef struct caar_dims {
   int nelem;   /* number of elements held by this handle (a rank's slice)      */
-  int nlev;    /* PLEV: fused kernels for 72 and 128 (tuned) and every other multiple of 8 up to 64, 80, 96, 112,
-                  120; any other value >= 2 runs on the generic reference-order kernel */
+  int nlev;    /* PLEV: fused kernel instances for 72 and 128 (tuned), every other multiple of 8 up to 64, 80, 96, 112,
+                  120; any other value in [2,128] runs on the next larger instance with masked padding levels;
+                  above 128 CAAR_MODE_FAST falls back to the reference-order kernel (caar_describe tells) */
   int np;      /* must be 4 */
   int qsize_d; /* QSIZE_D (1 in the reference) */
   int ntl;     /* NUM_TIME_LEVELS (3) */
@@ -167,7 +168,9 @@ int caar_set_params(caar_handle h, const caar_constants* c, const double dvv[16]
 int caar_set_vertical_coordinate(caar_handle h, int rsplit, const double* hybi);
 
 /* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all later work; NULL restores the
-   handle's own stream. Lets a torch program time the kernels with its own events. */
+   handle's own stream. Lets a torch program time the kernels with its own events. Ordering contract: everything
+   already queued through this handle on the previous stream is ordered BEFORE work submitted after the switch (an
+   event recorded on the old stream is waited on by the new one); the call itself does not block the host. */
 int caar_set_stream(caar_handle h, void* cuda_stream);
 
 /* Host <-> device copies of the selected fields (CAAR_F_* mask). Host pointers are caller-owned and
@@ -175,6 +178,11 @@ int caar_set_stream(caar_handle h, void* cuda_stream);
    return after the copies completed. */
 int caar_upload(caar_handle h, const caar_arrays* host, unsigned field_mask);
 int caar_download(caar_handle h, const caar_arrays* host, unsigned field_mask);
+
+/* The same for the element range [e0, e1) only: `host` points at arrays holding exactly those e1-e0 elements of each
+   selected field (a rank's window, a test's sample), in the layout above. */
+int caar_upload_range(caar_handle h, const caar_arrays* host, unsigned field_mask, int e0, int e1);
+int caar_download_range(caar_handle h, const caar_arrays* host, unsigned field_mask, int e0, int e1);
 
 /* ---- second host layout: Fortran flat pointers (SURVEY §8b "alt boundary") ----
    CAAR_LAYOUT_CXX is the layout above. CAAR_LAYOUT_F90 is the memory order of the Fortran arrays themselves
@@ -212,6 +220,11 @@ int caar_device_arrays(caar_handle h, caar_arrays* dev_out);
    handle's stream. Identical to calling the reference routine nsteps times with the same Control
    (PO/main.cpp:113-121: no time-level rotation between calls). mode = CAAR_MODE_*. */
 int caar_run(caar_handle h, const caar_control* ctl, int nsteps, int mode);
+/* Which kernel a caar_run in `mode` launches on this handle, as text in buf ("caar_fused_kernel<32,1,0>: nlev=30
+   (padded), ..."); *is_fused (may be NULL) = 1 for a fused instance, 0 for the reference-order kernel — for
+   CAAR_MODE_FAST that is the fallback for nlev > 128, also announced once on stderr. */
+int caar_describe(caar_handle h, int mode, char* buf, size_t len, int* is_fused);
+
 /* Time stepping on the resident state: nsteps evaluations with the reference's leapfrog
    rotation of the time levels after each one — TestData::update_time_levels, PO/data_structures.cpp:174-180
    (np1 <- nm1, nm1 <- n0, n0 <- old np1), the call the reference driver keeps next to its timed loop
@@ -247,6 +260,24 @@ int caar_euler_step(caar_handle h, int nets, int nete, int qn0, int qsize, doubl
    print_results_2norm takes the sqrt of (PO/compute_and_apply_rhs.cpp:384-398). Returned as SUMS OF
    SQUARES so that ranks can all-reduce them before the sqrt. Synchronous. */
 int caar_norms(caar_handle h, int tl, int nets, int nete, double sumsq[3]);
+
+/* Checksums of every array compute_and_apply_rhs writes, and two energy norms, over elements [nets,nete) — what the
+   ranks of a partitioned run all-reduce after the timed loop (north star: "final allreduce of field checksums and
+   energy norms"); the reference's own protocol prints only the three norms above (PO/compute_and_apply_rhs.cpp:372-399).
+   Field order: 0 dp3d(tl), 1 v(tl), 2 T(tl), 3 derived_eta_dot_dpdn, 4 derived_omega_p, 5 derived_phi, 6 derived_vn0.
+     sum, sumsq  plain sums in a fixed order (all-reduce with SUM; compare at ~1e-13 relative)
+     bits        sum of the IEEE-754 bit patterns mod 2^64: exact and order-independent, so two runs (or a run and the
+                 bit-exact CPU reference) hold identical data iff these agree — all-reduce as 64-bit integers with SUM
+     energy      { sum spheremp*0.5*(u^2+v^2)*dp3d, sum spheremp*cp*T*dp3d } at time level tl: the kinetic and internal
+                 energy integrands of the reference's diagnostics (F/routine_extracted.F90:396-410)
+   Synchronous. */
+typedef struct caar_checksum {
+  double sum[7];
+  double sumsq[7];
+  unsigned long long bits[7];
+  double energy[2];
+} caar_checksum;
+int caar_checksums(caar_handle h, int tl, int nets, int nete, caar_checksum* out);
 
 /* ---- the hot path on HOST arrays (what Homme::compute_and_apply_rhs(TestData&) means to its caller,
    PO/compute_and_apply_rhs.hpp:9, called from the timed loop PO/main.cpp:113-121) ---- */

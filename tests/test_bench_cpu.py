@@ -12,7 +12,7 @@ def _run(env_extra=None):
     env = dict(os.environ)
     env.update(env_extra or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                           "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+                           "--warmup", "1", "--nelem", "512"], capture_output=True, text=True, env=env, timeout=600)
 
 
 def test_reference_arm_json_line():
@@ -27,7 +27,7 @@ def test_reference_arm_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["sampled"] is False and d["config"]["elements_timed"] == 512
 
 
 def test_reference_arm_other_ranks_are_silent():

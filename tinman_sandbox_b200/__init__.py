@@ -15,11 +15,11 @@ the built extension.
 from .capi import (  # noqa: F401
     Caar, CaarError, FIELD_NAMES, MUTATED_FIELDS, MODE_FAST, MODE_STRICT, lib_path, load_library,
     field_shape, compute_and_apply_rhs, saxpby_host, EXPORTED_SYMBOLS, HOST_ZERO_COPY, host_register,
-    host_unregister,
+    host_unregister, CHECKSUM_FIELDS,
 )
 
 __all__ = [
     "Caar", "CaarError", "FIELD_NAMES", "MUTATED_FIELDS", "MODE_FAST", "MODE_STRICT", "lib_path",
     "load_library", "field_shape", "compute_and_apply_rhs", "saxpby_host", "EXPORTED_SYMBOLS",
-    "HOST_ZERO_COPY", "host_register", "host_unregister",
+    "HOST_ZERO_COPY", "host_register", "host_unregister", "CHECKSUM_FIELDS",
 ]

@@ -38,8 +38,10 @@ EXPORTED_SYMBOLS = (
     "caar_update_time_levels", "caar_extra_count", "caar_extra_upload", "caar_extra_download", "caar_euler_step",
     "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
-    "caar_saxpby_host",
+    "caar_saxpby_host", "caar_checksums", "caar_upload_range", "caar_download_range", "caar_describe",
 )
+CHECKSUM_FIELDS = ("elem_state_dp3d", "elem_state_v", "elem_state_T", "elem_derived_eta_dot_dpdn",
+                   "elem_derived_omega_p", "elem_derived_phi", "elem_derived_vn0")
 
 
 class CaarError(RuntimeError):
@@ -56,6 +58,11 @@ class Arrays(C.Structure):
 
 class Constants(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("rrearth", "eta_ave_w", "cp", "Rwater_vapor", "Rgas", "kappa")]
+
+
+class Checksum(C.Structure):
+    _fields_ = [("sum", C.c_double * 7), ("sumsq", C.c_double * 7), ("bits", C.c_ulonglong * 7),
+                ("energy", C.c_double * 2)]
 
 
 class Control(C.Structure):
@@ -132,6 +139,10 @@ def load_library():
     lib.caar_timer_start.argtypes = [C.c_void_p]
     lib.caar_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.caar_norms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.caar_describe.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+    lib.caar_checksums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Checksum)]
+    lib.caar_upload_range.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int, C.c_int]
+    lib.caar_download_range.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int, C.c_int]
     lib.caar_compute_and_apply_rhs_host.argtypes = [C.POINTER(Dims), C.POINTER(Arrays), C.POINTER(Control),
                                                     C.POINTER(Constants), C.POINTER(C.c_double), C.c_double,
                                                     C.POINTER(C.c_double), C.c_int, C.c_int]
@@ -268,6 +279,43 @@ class Caar:
         names = FIELD_NAMES if names is None else names
         st = _arrays_struct(arrays, names, self.shape_args)
         _check(self.lib, self.lib.caar_download(self.h, C.byref(st), _mask(names)), "caar_download")
+
+    def _range_struct(self, arrays, names, e0, e1):
+        E, L, Q, ntl = self.shape_args
+        return _arrays_struct(arrays, names, (e1 - e0, L, Q, ntl))
+
+    def upload_range(self, arrays: dict, e0, e1, names=None):
+        """arrays hold ONLY elements [e0,e1) of each field (caar_upload_range)."""
+        names = FIELD_NAMES if names is None else names
+        st = self._range_struct(arrays, names, e0, e1)
+        _check(self.lib, self.lib.caar_upload_range(self.h, C.byref(st), _mask(names), e0, e1), "caar_upload_range")
+
+    def download_range(self, e0, e1, names=MUTATED_FIELDS, arrays=None):
+        """-> dict of arrays holding elements [e0,e1) of the named fields (caar_download_range)."""
+        names = FIELD_NAMES if names is None else names
+        E, L, Q, ntl = self.shape_args
+        if arrays is None:
+            arrays = {n: np.empty(field_shape(n, e1 - e0, L, Q, ntl)) for n in names}
+        st = self._range_struct(arrays, names, e0, e1)
+        _check(self.lib, self.lib.caar_download_range(self.h, C.byref(st), _mask(names), e0, e1), "caar_download_range")
+        return arrays
+
+    def checksums(self, tl=None, nets=None, nete=None):
+        """caar_checksums -> dict(sum, sumsq: float64[7]; bits: uint64[7]; energy: float64[2]); field order
+        CHECKSUM_FIELDS. All-reduce sum/sumsq/energy with SUM and bits as 64-bit integers with SUM."""
+        out = Checksum()
+        tl = self.control.np1 if tl is None else tl
+        nets = self.control.nets if nets is None else nets
+        nete = self.control.nete if nete is None else nete
+        _check(self.lib, self.lib.caar_checksums(self.h, tl, nets, nete, C.byref(out)), "caar_checksums")
+        return {"sum": np.array(out.sum[:]), "sumsq": np.array(out.sumsq[:]),
+                "bits": np.array(out.bits[:], dtype=np.uint64), "energy": np.array(out.energy[:])}
+
+    def describe(self, mode=MODE_FAST):
+        """-> (text, is_fused): which kernel compute_and_apply_rhs launches in `mode` (caar_describe)."""
+        buf, flag = C.create_string_buffer(256), C.c_int()
+        _check(self.lib, self.lib.caar_describe(self.h, mode, buf, 256, C.byref(flag)), "caar_describe")
+        return buf.value.decode(), bool(flag.value)
 
     def device_pointers(self):
         st = Arrays()

@@ -5,6 +5,20 @@
 #include "caar_device.cuh"
 
 namespace caar {
+
+// number of SMs of the current device (cached per device ordinal): grid caps are multiples of it
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 namespace {
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -64,6 +78,96 @@ __global__ void __launch_bounds__(1024) norms_final_kernel(const double* partial
   }
 }
 
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  unsigned long long s = 0;
+  if (w == 0) {
+    s = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  }
+  return s;  // valid in warp 0
+}
+
+// Checksums of the seven arrays compute_and_apply_rhs writes, one CTA per element:
+// partial[e][f] = { sum, sum of squares } for f = dp3d(tl), v(tl), T(tl), eta_dot_dpdn, omega_p, phi, vn0,
+// partial[e][7] = { KE, IE }: sum of spheremp*0.5*(u^2+v^2)*dp3d and spheremp*cp*T*dp3d at time level tl (the
+// integrands of the reference's energy diagnostics, F/routine_extracted.F90:396-410), bits[e][f] = sum of the IEEE
+// bit patterns mod 2^64 (exact and order-independent: equal data <=> equal sums, up to 2^-64 collisions).
+__global__ void __launch_bounds__(256) checksums_partial_kernel(const KernelArgs A, int tl, int nets, double cp,
+                                                                 double* partial /*[nelem][8][2]*/,
+                                                                 unsigned long long* bits /*[nelem][7]*/) {
+  __shared__ double red[8];
+  __shared__ unsigned long long redu[8];
+  const size_t e = (size_t)(nets + blockIdx.x);
+  const int lf = A.nlev * PTS;
+  const double* f[7] = {A.dp3d + (e * A.ntl + tl) * (size_t)lf, A.v + (e * A.ntl + tl) * (size_t)lf * 2,
+                        A.T + (e * A.ntl + tl) * (size_t)lf,    A.eta_dot_dpdn + e * (size_t)(lf + PTS),
+                        A.omega_p + e * (size_t)lf,             A.phi + e * (size_t)lf,
+                        A.vn0 + e * (size_t)lf * 2};
+  const int n[7] = {lf, 2 * lf, lf, lf + PTS, lf, lf, 2 * lf};
+#pragma unroll 1
+  for (int a = 0; a < 7; ++a) {
+    double s = 0, q = 0;
+    unsigned long long b = 0;
+    for (int i = threadIdx.x; i < n[a]; i += blockDim.x) {
+      const double x = f[a][i];
+      s += x;
+      q = fma(x, x, q);
+      b += (unsigned long long)__double_as_longlong(x);
+    }
+    s = block_sum(s, red);
+    q = block_sum(q, red);
+    b = block_sum_u64(b, redu);
+    if (threadIdx.x == 0) {
+      partial[(e * 8 + a) * 2 + 0] = s;
+      partial[(e * 8 + a) * 2 + 1] = q;
+      bits[e * 7 + a] = b;
+    }
+  }
+  double ke = 0, ie = 0;
+  const double2* v = reinterpret_cast<const double2*>(f[1]);
+  for (int i = threadIdx.x; i < lf; i += blockDim.x) {
+    const double w = A.spheremp[e * PTS + (i & 15)] * f[0][i];
+    const double2 u = v[i];
+    ke = fma(w * 0.5, fma(u.x, u.x, u.y * u.y), ke);
+    ie = fma(w * cp, f[2][i], ie);
+  }
+  ke = block_sum(ke, red);
+  ie = block_sum(ie, red);
+  if (threadIdx.x == 0) {
+    partial[(e * 8 + 7) * 2 + 0] = ke;
+    partial[(e * 8 + 7) * 2 + 1] = ie;
+  }
+}
+
+// one CTA: fixed-order reduction over [nets, nete) of the 16 doubles and 7 bit sums per element
+__global__ void __launch_bounds__(1024) checksums_final_kernel(const double* partial, const unsigned long long* bits,
+                                                                int nets, int nete, double* out16,
+                                                                unsigned long long* out7) {
+  __shared__ double red[32];
+  __shared__ unsigned long long redu[32];
+#pragma unroll 1
+  for (int c = 0; c < 16; ++c) {
+    double s = 0;
+    for (int e = nets + threadIdx.x; e < nete; e += blockDim.x) s += partial[(size_t)e * 16 + c];
+    const double r = block_sum(s, red);
+    if (threadIdx.x == 0) out16[c] = r;
+  }
+#pragma unroll 1
+  for (int c = 0; c < 7; ++c) {
+    unsigned long long s = 0;
+    for (int e = nets + threadIdx.x; e < nete; e += blockDim.x) s += bits[(size_t)e * 7 + c];
+    const unsigned long long r = block_sum_u64(s, redu);
+    if (threadIdx.x == 0) out7[c] = r;
+  }
+}
+
 // grid-stride, 2 doubles per thread per trip (LDG.128/STG.128), x read-modify-write, y read-only
 __global__ void __launch_bounds__(512) saxpby_kernel(double a, double b, double* __restrict__ x,
                                                       const double* __restrict__ y, size_t n2, size_t n) {
@@ -90,6 +194,13 @@ __global__ void __launch_bounds__(512) saxpby_kernel(double a, double b, double*
     x2[i] = xv;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) x[n - 1] = a * x[n - 1] + b * y[n - 1];
+}
+
+// pointers that are 8- but not 16-byte aligned (a sub-array offset): plain 64-bit accesses
+__global__ void __launch_bounds__(512) saxpby_scalar_kernel(double a, double b, double* __restrict__ x,
+                                                             const double* __restrict__ y, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = a * x[i] + b * __ldg(y + i);
 }
 
 // ---- host-layout conversion for the Fortran (F90 flat pointer) boundary --------------------------------------
@@ -140,7 +251,7 @@ cudaError_t launch_relayout(double* cxx, double* f90, size_t nblocks, int kind, 
   if (nblocks == 0) return cudaSuccess;
   const size_t n = nblocks * (16u << kind);
   size_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > (size_t)sm_count() * 32) blocks = (size_t)sm_count() * 32;
   relayout_kernel<<<(unsigned)blocks, 256, 0, s>>>(cxx, f90, nblocks, kind, to_cxx ? 1 : 0, q_dim, nlev, blk0);
   return cudaGetLastError();
 }
@@ -148,7 +259,7 @@ cudaError_t launch_relayout(double* cxx, double* f90, size_t nblocks, int kind, 
 cudaError_t launch_reciprocal(double* out, const double* in, size_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   size_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > (size_t)sm_count() * 32) blocks = (size_t)sm_count() * 32;
   reciprocal_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, in, n);
   return cudaGetLastError();
 }
@@ -165,9 +276,19 @@ cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t
   const size_t n2 = n / 2;
   size_t blocks = (n2 + 512 * 4 - 1) / (512 * 4);
   if (blocks < 1) blocks = 1;
-  const size_t cap = 148 * 4 * 8;  // a few waves of 4 resident CTAs per SM
+  const size_t cap = (size_t)sm_count() * 4 * 8;  // a few waves of 4 resident CTAs per SM
   if (blocks > cap) blocks = cap;
-  saxpby_kernel<<<(unsigned)blocks, 512, 0, s>>>(a, b, x, y, n2, n);
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)  // not double2-aligned
+    saxpby_scalar_kernel<<<(unsigned)blocks, 512, 0, s>>>(a, b, x, y, n);
+  else
+    saxpby_kernel<<<(unsigned)blocks, 512, 0, s>>>(a, b, x, y, n2, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_checksums(const KernelArgs& a, int tl, int nets, int nete, double cp, double* partial,
+                             unsigned long long* bits, double* out16, unsigned long long* out7, cudaStream_t s) {
+  if (nete > nets) checksums_partial_kernel<<<nete - nets, 256, 0, s>>>(a, tl, nets, cp, partial, bits);
+  checksums_final_kernel<<<1, 1024, 0, s>>>(partial, bits, nets, nete, out16, out7);
   return cudaGetLastError();
 }
 

@@ -60,9 +60,10 @@ struct caar_handle_s {
   bool params_set;
   caar_constants c;
   double dvv[16], ps0, hyai0;
-  double* partial;    // [nelem][3] device
-  double* out3;       // [3] device
-  double* out3_host;  // [3] pinned
+  double* partial;    // [nelem][16] device: norms use [nelem][3], checksums [nelem][8][2]
+  unsigned long long* bits;  // [nelem][7] device (checksums)
+  double* out3;       // [16 doubles + 7 u64] device: results of the norm / checksum reductions
+  double* out3_host;  // the same, pinned
   cudaEvent_t ev0, ev1;
   long long launches;
   caar::TmaMaps* tma;  // TMA descriptors of the device mirrors (nlev with a TMA-pipelined kernel only)
@@ -111,8 +112,17 @@ int validate_control(const caar_handle_s* h, const caar_control* ctl) {
 // the fused kernels cover the vertically Lagrangian branch, and the Eulerian one where launch_fused says so;
 // everything else runs on the generic reference-order kernel (still on the GPU)
 bool uses_fused(const caar_handle_s* h, int mode) {
-  return mode == CAAR_MODE_FAST && caar::fused_supports(h->dims.nlev) &&
-         (h->rsplit > 0 || caar::fused_supports_eulerian(h->dims.nlev));
+  const bool fused = mode == CAAR_MODE_FAST && caar::fused_supports(h->dims.nlev) &&
+                     (h->rsplit > 0 || caar::fused_supports_eulerian(h->dims.nlev));
+  if (mode == CAAR_MODE_FAST && !fused) {  // never silent: the reference-order kernel is ~6x slower
+    static bool told = false;
+    if (!told) {
+      told = true;
+      fprintf(stderr, "[caar] CAAR_MODE_FAST: no fused kernel instance for nlev=%d (instances cover nlev <= 128); "
+                      "running the reference-order kernel instead (see caar_describe)\n", h->dims.nlev);
+    }
+  }
+  return fused;
 }
 // eta_dot_dpdn travels when the kernel really updates it: the reference-order kernel always does (+= 0 included),
 // the fused kernels only on the Eulerian branch
@@ -192,9 +202,10 @@ int caar_create(caar_handle* out, const caar_dims* dims, int device) {
     e = cudaMalloc(&h->dev[f], bytes);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->dev[f], 0, bytes, h->own_stream);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&h->partial, (size_t)dims->nelem * 3 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->out3, 3 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMallocHost(&h->out3_host, 3 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->partial, (size_t)dims->nelem * 16 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->bits, (size_t)dims->nelem * 7 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&h->out3, 23 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->out3_host, 23 * sizeof(double));
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
   if (e != cudaSuccess) {
     const int code = fail(e == cudaErrorMemoryAllocation ? CAAR_ERR_NOMEM : CAAR_ERR_CUDA, "caar_create: %s",
@@ -227,6 +238,7 @@ int caar_destroy(caar_handle h) {
   for (int f = 0; f < CAAR_NUM_FIELDS; ++f)
     if (h->dev[f]) cudaFree(h->dev[f]);
   if (h->partial) cudaFree(h->partial);
+  if (h->bits) cudaFree(h->bits);
   if (h->out3) cudaFree(h->out3);
   if (h->stage) cudaFree(h->stage);
   for (int x = 0; x < 2; ++x)
@@ -274,7 +286,13 @@ int caar_set_vertical_coordinate(caar_handle h, int rsplit, const double* hybi) 
 
 int caar_set_stream(caar_handle h, void* cuda_stream) {
   if (!h) return fail(CAAR_ERR_INVALID, "null handle");
-  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  if (next != h->stream) {  // work already queued on the old stream stays ordered before whatever follows on the new one
+    DeviceGuard guard(h->device);
+    CU_TRY(cudaEventRecord(h->ev_fence, h->stream));
+    CU_TRY(cudaStreamWaitEvent(next, h->ev_fence, 0));
+  }
+  h->stream = next;
   return CAAR_OK;
 }
 
@@ -293,6 +311,32 @@ static int copy_fields(caar_handle h, const caar_arrays* host, unsigned mask, bo
   }
   CU_TRY(cudaStreamSynchronize(h->stream));
   return CAAR_OK;
+}
+
+// element range [e0,e1) of the selected fields <-> host arrays that hold ONLY that range
+static int copy_range(caar_handle h, const caar_arrays* host, unsigned mask, int e0, int e1, bool to_device) {
+  if (!h || !host) return fail(CAAR_ERR_INVALID, "null argument");
+  if (e0 < 0 || e1 > h->dims.nelem || e0 > e1) return fail(CAAR_ERR_INVALID, "element range [%d,%d) outside [0,%d)", e0, e1, h->dims.nelem);
+  DeviceGuard guard(h->device);
+  double* const* tab = as_table(host);
+  for (int f = 0; f < CAAR_NUM_FIELDS; ++f) {
+    if (!(mask & (1u << f))) continue;
+    if (!tab[f]) return fail(CAAR_ERR_INVALID, "host pointer of field %d is null", f);
+    const size_t per_elem = field_count(h->dims, f) / h->dims.nelem;
+    const size_t bytes = per_elem * (size_t)(e1 - e0) * sizeof(double);
+    double* dev = h->dev[f] + per_elem * (size_t)e0;
+    if (to_device) CU_TRY(cudaMemcpyAsync(dev, tab[f], bytes, cudaMemcpyHostToDevice, h->stream));
+    else CU_TRY(cudaMemcpyAsync(tab[f], dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return CAAR_OK;
+}
+
+int caar_upload_range(caar_handle h, const caar_arrays* host, unsigned mask, int e0, int e1) {
+  return copy_range(h, host, mask, e0, e1, true);
+}
+int caar_download_range(caar_handle h, const caar_arrays* host, unsigned mask, int e0, int e1) {
+  return copy_range(h, host, mask, e0, e1, false);
 }
 
 int caar_upload(caar_handle h, const caar_arrays* host, unsigned mask) { return copy_fields(h, host, mask, true); }
@@ -385,6 +429,23 @@ int caar_host_unregister(void* ptr) {
 int caar_device_arrays(caar_handle h, caar_arrays* out) {
   if (!h || !out) return fail(CAAR_ERR_INVALID, "null argument");
   std::memcpy(out, h->dev, sizeof h->dev);
+  return CAAR_OK;
+}
+
+int caar_describe(caar_handle h, int mode, char* buf, size_t len, int* is_fused) {
+  if (!h || !buf || !len) return fail(CAAR_ERR_INVALID, "null argument");
+  if (mode != CAAR_MODE_FAST && mode != CAAR_MODE_STRICT) return fail(CAAR_ERR_INVALID, "mode=%d", mode);
+  const int nlev = h->dims.nlev;
+  const bool fused = mode == CAAR_MODE_FAST && caar::fused_supports(nlev);
+  if (fused)
+    snprintf(buf, len, "caar_fused_kernel<%d,%d,%d>: nlev=%d%s, %d CTA(s) of %d threads per element",
+             caar::fused_instance_levels(nlev), caar::fused_instance_cluster(nlev), h->rsplit == 0 ? 1 : 0, nlev,
+             caar::fused_instance_levels(nlev) != nlev ? " (padded)" : "", caar::fused_instance_cluster(nlev),
+             4 * caar::fused_instance_levels(nlev) / caar::fused_instance_cluster(nlev));
+  else
+    snprintf(buf, len, "caar_strict_kernel: nlev=%d, one 512-thread CTA per element%s", nlev,
+             mode == CAAR_MODE_FAST ? " (FALLBACK: no fused instance for this nlev)" : "");
+  if (is_fused) *is_fused = fused ? 1 : 0;
   return CAAR_OK;
 }
 
@@ -574,18 +635,37 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
   CU_TRY(cudaEventRecord(h->ev_fence, h->stream));
   CU_TRY(cudaStreamWaitEvent(h->s_in, h->ev_fence, 0));
   caar::KernelArgs a = make_args(h, ctl);
-  for (int c = 0; c < nchunks; ++c) {
+  // On any failure inside the pipeline the three streams are drained before returning, so that no DMA is still
+  // reading or writing the caller's arrays when the caller sees the error (the host arrays may then hold the results
+  // of the chunks that completed: the call is NOT transactional).
+  cudaError_t ce = cudaSuccess;
+  const char* what = "";
+#define PIPE_TRY(expr)            \
+  if (ce == cudaSuccess) {        \
+    ce = (expr);                  \
+    if (ce != cudaSuccess) what = #expr; \
+  }
+  for (int c = 0; c < nchunks && ce == cudaSuccess; ++c) {
     const int e0 = ctl->nets + c * chunk, e1 = (e0 + chunk < ctl->nete) ? e0 + chunk : ctl->nete;
-    for (int i = 0; i < ni; ++i) CU_TRY(copy_slice(in[i], h->dev[in[i].f], tab[in[i].f], e0, e1, true, h->s_in));
-    CU_TRY(cudaEventRecord(h->chunk_ev[2 * c], h->s_in));
-    CU_TRY(cudaStreamWaitEvent(h->stream, h->chunk_ev[2 * c], 0));
+    for (int i = 0; i < ni; ++i) PIPE_TRY(copy_slice(in[i], h->dev[in[i].f], tab[in[i].f], e0, e1, true, h->s_in));
+    PIPE_TRY(cudaEventRecord(h->chunk_ev[2 * c], h->s_in));
+    PIPE_TRY(cudaStreamWaitEvent(h->stream, h->chunk_ev[2 * c], 0));
     a.nets = e0;
     a.nete = e1;
-    CU_TRY(fast ? caar::launch_fused(a, h->stream) : caar::launch_strict(a, h->stream));
-    ++h->launches;
-    CU_TRY(cudaEventRecord(h->chunk_ev[2 * c + 1], h->stream));
-    CU_TRY(cudaStreamWaitEvent(h->s_out, h->chunk_ev[2 * c + 1], 0));
-    for (int i = 0; i < no; ++i) CU_TRY(copy_slice(out[i], h->dev[out[i].f], tab[out[i].f], e0, e1, false, h->s_out));
+    PIPE_TRY(fast ? caar::launch_fused(a, h->stream) : caar::launch_strict(a, h->stream));
+    if (ce == cudaSuccess) ++h->launches;
+    PIPE_TRY(cudaEventRecord(h->chunk_ev[2 * c + 1], h->stream));
+    PIPE_TRY(cudaStreamWaitEvent(h->s_out, h->chunk_ev[2 * c + 1], 0));
+    for (int i = 0; i < no; ++i) PIPE_TRY(copy_slice(out[i], h->dev[out[i].f], tab[out[i].f], e0, e1, false, h->s_out));
+  }
+#undef PIPE_TRY
+  if (ce != cudaSuccess) {
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->s_out);
+    cudaGetLastError();
+    return fail(ce == cudaErrorMemoryAllocation ? CAAR_ERR_NOMEM : CAAR_ERR_CUDA, "caar_run_host: %s failed: %s", what,
+                cudaGetErrorString(ce));
   }
   CU_TRY(cudaStreamSynchronize(h->s_out));
   CU_TRY(cudaStreamSynchronize(h->stream));
@@ -722,6 +802,27 @@ int caar_norms(caar_handle h, int tl, int nets, int nete, double sumsq[3]) {
   CU_TRY(cudaMemcpyAsync(h->out3_host, h->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < 3; ++i) sumsq[i] = h->out3_host[i];
+  return CAAR_OK;
+}
+
+int caar_checksums(caar_handle h, int tl, int nets, int nete, caar_checksum* out) {
+  if (!h || !out) return fail(CAAR_ERR_INVALID, "null argument");
+  if (tl < 0 || tl >= h->dims.ntl) return fail(CAAR_ERR_INVALID, "time level %d", tl);
+  if (nets < 0 || nete > h->dims.nelem || nets > nete) return fail(CAAR_ERR_INVALID, "element range [%d,%d)", nets, nete);
+  DeviceGuard guard(h->device);
+  const caar::KernelArgs a = make_args(h, nullptr);
+  unsigned long long* out7 = reinterpret_cast<unsigned long long*>(h->out3 + 16);
+  CU_TRY(caar::launch_checksums(a, tl, nets, nete, h->c.cp, h->partial, h->bits, h->out3, out7, h->stream));
+  h->launches += (nete > nets) ? 2 : 1;
+  CU_TRY(cudaMemcpyAsync(h->out3_host, h->out3, 23 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  for (int f = 0; f < 7; ++f) {
+    out->sum[f] = h->out3_host[2 * f];
+    out->sumsq[f] = h->out3_host[2 * f + 1];
+    std::memcpy(&out->bits[f], &h->out3_host[16 + f], sizeof(unsigned long long));
+  }
+  out->energy[0] = h->out3_host[14];
+  out->energy[1] = h->out3_host[15];
   return CAAR_OK;
 }
 

@@ -52,8 +52,9 @@ struct KernelArgs {
   int pf_dist;
 };
 
-// TMA tensor maps over the level-field arrays viewed as 2-D [rows of 128 B][16 doubles], box = one
-// element's slice, SWIZZLE_128B (conflict-free shared-memory tiles). Built once per handle.
+// TMA tensor maps over the level-field arrays viewed as 3-D [slice][rows of 128 B][16 doubles] (slice = element x
+// time level / tracer, rows = levels), box = one CTA's slab of one slice, SWIZZLE_128B (conflict-free shared-memory
+// tiles). Built once per handle.
 struct alignas(64) TmaMaps {
   CUtensorMap dp3d, T, v, vn0, pecnd, omega_p, phi, Qdp;
 };
@@ -65,6 +66,8 @@ cudaError_t launch_strict(const KernelArgs& a, cudaStream_t s);
 cudaError_t launch_fused(const KernelArgs& a, cudaStream_t s);
 bool fused_supports(int nlev);
 bool fused_supports_eulerian(int nlev);  // rsplit == 0 on the fused path
+int fused_instance_levels(int nlev);     // compiled level count that serves nlev (>= nlev), 0 = none
+int fused_instance_cluster(int nlev);    // CTAs per element of that instance
 cudaError_t launch_fused_more(const KernelArgs& a, cudaStream_t s);  // level counts other than 72 / 128
 size_t strict_smem_bytes(int nlev);
 
@@ -78,5 +81,9 @@ cudaError_t launch_reciprocal(double* out, const double* in, size_t n, cudaStrea
 cudaError_t launch_euler_step(const KernelArgs& a, const double* vstar, double* qtens, int nets, int nete, int qn0,
                               int qsize, double dt, bool strict, cudaStream_t s);
 cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t n, cudaStream_t s);
+// checksums of the seven mutated arrays + energy norms (caar_aux.cu); partial [nelem][8][2], bits [nelem][7]
+cudaError_t launch_checksums(const KernelArgs& a, int tl, int nets, int nete, double cp, double* partial,
+                             unsigned long long* bits, double* out16, unsigned long long* out7, cudaStream_t s);
+int sm_count();  // SMs of the current device
 
 }  // namespace caar

@@ -178,7 +178,7 @@ cudaError_t launch_euler_step(const KernelArgs& a, const double* vstar, double* 
   const long long rows = (long long)(nete - nets) * a.nlev;
   long long groups = (rows + 63) / 64;
   static const int waves = [] { const char* v = getenv("CAAR_EULER_WAVES"); return v ? atoi(v) : 2; }();
-  const long long cap = 148LL * 3 * (waves > 0 ? waves : 1);  // persistent CTAs: a few waves of 3 resident CTAs per SM
+  const long long cap = (long long)sm_count() * 3 * (waves > 0 ? waves : 1);  // persistent CTAs: a few waves of 3 resident CTAs per SM
   const unsigned blocks = (unsigned)(waves > 0 && groups > cap ? cap : groups);
   if (strict)
     euler_step_kernel<true><<<blocks, 256, 0, s>>>(e);

@@ -1,6 +1,7 @@
 // caar_fused.cu — dispatch of CAAR_MODE_FAST to the fused kernel instances (caar_fused_kernel.cuh), the TMA tensor
 // maps they use, and the instances for the two level counts of the reference configurations (nlev = 72, 128).
-// Other level counts that are multiples of 8 are instantiated in caar_fused_more.cu.
+// The other instances (multiples of 8 up to 64, 80, 96, 112, 120) are in caar_fused_more.cu; a level count without
+// an instance of its own runs on the next larger one with padding levels (instance_for()).
 #include "caar_fused_kernel.cuh"
 
 namespace caar {
@@ -17,29 +18,33 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   }
   const encode_t encode = reinterpret_cast<encode_t>(fn);
   const cuuint64_t E = (cuuint64_t)a.nelem, L = (cuuint64_t)a.nlev, ntl = (cuuint64_t)a.ntl;
-  const cuuint32_t LB = (cuuint32_t)(a.nlev / (cluster_for(a.nlev) > 0 ? cluster_for(a.nlev) : 1));  // levels per CTA = box rows
-  struct Spec { CUtensorMap* m; const void* base; cuuint64_t rows; cuuint32_t box; const char* name; };
+  const int inst = instance_for(a.nlev);  // compiled level count serving this nlev (>= nlev)
+  const cuuint32_t LB = (cuuint32_t)(inst / (cluster_for(inst) > 0 ? cluster_for(inst) : 1));  // levels per CTA = box rows
+  // every array as [slices][rows][16 doubles]: rows = the levels of one element (x time level, tracer ...) slice, x2 for
+  // the interleaved (u,v) fields. A box that sticks out of its slice (padding levels) is zero-filled on load and
+  // clipped on store, and its missing rows cost no HBM traffic.
+  struct Spec { CUtensorMap* m; const void* base; cuuint64_t slices; cuuint64_t rows; cuuint32_t box; const char* name; };
   const Spec specs[8] = {
-      {&out->Qdp, a.Qdp, E * (cuuint64_t)a.qsize_d * 2 * L, LB, "Qdp"},
-      {&out->dp3d, a.dp3d, E * ntl * L, LB, "dp3d"},
-      {&out->T, a.T, E * ntl * L, LB, "T"},
-      {&out->v, a.v, E * ntl * L * 2, 2 * LB, "v"},
-      {&out->vn0, a.vn0, E * L * 2, 2 * LB, "vn0"},
-      {&out->pecnd, a.pecnd, E * L, LB, "pecnd"},
-      {&out->omega_p, a.omega_p, E * L, LB, "omega_p"},
-      {&out->phi, a.phi, E * L, LB, "phi"},
+      {&out->Qdp, a.Qdp, E * (cuuint64_t)a.qsize_d * 2, L, LB, "Qdp"},
+      {&out->dp3d, a.dp3d, E * ntl, L, LB, "dp3d"},
+      {&out->T, a.T, E * ntl, L, LB, "T"},
+      {&out->v, a.v, E * ntl, 2 * L, 2 * LB, "v"},
+      {&out->vn0, a.vn0, E, 2 * L, 2 * LB, "vn0"},
+      {&out->pecnd, a.pecnd, E, L, LB, "pecnd"},
+      {&out->omega_p, a.omega_p, E, L, LB, "omega_p"},
+      {&out->phi, a.phi, E, L, LB, "phi"},
   };
   for (const Spec& sp : specs) {
-    const cuuint64_t gdim[2] = {16, sp.rows};
-    const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {16, sp.box};
-    const cuuint32_t estride[2] = {1, 1};
-    if (sp.box > 256 || sp.rows >= (1ull << 31)) {
-      snprintf(err, errlen, "tensor map %s: box %u rows / %llu rows out of range", sp.name, sp.box,
-               (unsigned long long)sp.rows);
+    const cuuint64_t gdim[3] = {16, sp.rows, sp.slices};
+    const cuuint64_t gstride[2] = {128, sp.rows * 128};
+    const cuuint32_t box[3] = {16, sp.box, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    if (sp.box > 256 || sp.slices >= (1ull << 31)) {
+      snprintf(err, errlen, "tensor map %s: box of %u rows / %llu slices out of range", sp.name, sp.box,
+               (unsigned long long)sp.slices);
       return 1;
     }
-    const CUresult r = encode(sp.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(sp.base), gdim, gstride, box,
+    const CUresult r = encode(sp.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(sp.base), gdim, gstride, box,
                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -50,9 +55,12 @@ int build_tma_maps(TmaMaps* out, const KernelArgs& a, char* err, size_t errlen) 
   return 0;
 }
 
-bool fused_supports_eulerian(int nlev) { return cluster_for(nlev) > 0; }
+bool fused_supports_eulerian(int nlev) { return instance_for(nlev) > 0; }
 
-bool fused_supports(int nlev) { return cluster_for(nlev) > 0; }
+bool fused_supports(int nlev) { return instance_for(nlev) > 0; }
+
+int fused_instance_levels(int nlev) { return instance_for(nlev); }
+int fused_instance_cluster(int nlev) { return instance_for(nlev) ? cluster_for(instance_for(nlev)) : 0; }
 
 cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
   KernelArgs a = a0;
@@ -63,10 +71,11 @@ cudaError_t launch_fused(const KernelArgs& a0, cudaStream_t s) {
   // default distance: nlev=72 (CTA triples) -> 74 elements (16: 0.921, 32: 0.937, 74: 0.946, 148: 0.944 of the
   // measured peak); nlev=128 (CTA pairs) -> 32 (flat optimum 4...48, 0.74 at 148).
   // Sweeps: profiles/README.md.
-  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : (a.nlev == 72 ? 74 : 32));
-  switch (a.nlev) {
+  a.pf_dist = a0.pf_dist < 0 ? 0 : (pf_env >= 0 ? pf_env : (a.nlev == 72 ? sm_count() / 2 : 32));  // 74 on a 148-SM B200
+  switch (instance_for(a.nlev)) {
     case 72: return launch_nlev<72>(a, s);
     case 128: return launch_nlev<128>(a, s);
+    case 0: return cudaErrorInvalidValue;
   }
   return launch_fused_more(a, s);
 }

@@ -55,12 +55,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// 2-D tiled TMA load: rows [row, row+box) x 16 doubles of the array behind `map` -> swizzled smem tile
-__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* map, int row, uint64_t* bar) {
+// 3-D tiled TMA load: rows [row, row+box) x 16 doubles of slice `slice` of the array behind `map` -> swizzled smem
+// tile. The arrays are described as [slice][row][16 doubles] (slice = element x time level ..., row = level, or level x
+// component for (u,v)); rows beyond the slice's extent are zero-filled in shared memory and never read from HBM, which
+// is what lets an instance compiled for L levels serve any nlev <= L.
+__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* map, int row, int slice, uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
           smem_u32(dst)),
-      "l"(map), "r"(0), "r"(row), "r"(smem_u32(bar))
+      "l"(map), "r"(0), "r"(row), "r"(slice), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
@@ -74,10 +77,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
   } while (!done);
 }
-// 2-D tiled TMA store: swizzled smem tile -> rows [row, row+box) of the array behind `map`
-__device__ __forceinline__ void tma_store(const CUtensorMap* map, int row, const void* src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0),
-               "r"(row), "r"(smem_u32(src))
+// 3-D tiled TMA store: swizzled smem tile -> rows [row, row+box) of slice `slice`; rows beyond the slice's extent
+// are clipped (not written)
+__device__ __forceinline__ void tma_store(const CUtensorMap* map, int row, int slice, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(0),
+               "r"(row), "r"(slice), "r"(smem_u32(src))
                : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
@@ -284,17 +288,24 @@ __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int
 #define CAAR_REGS_SMALL 96  // CL = 1, nlev = 72: 2 CTAs of 9 warps per SM = 5 warps on the fullest SMSP: 16384/(5*32) = 102 -> 96
 #endif
 
-// CTAs per element (cluster size) for every level count with a fused instance; 0 = none (the reference-order kernel
-// serves it). Levels per CTA = nlev / cluster_for(nlev), a multiple of 8 (a warp scans 8 levels).
+// CTAs per element (cluster size) for every level count with a compiled instance; 0 = none.
+// Levels per CTA = nlev / cluster_for(nlev), a multiple of 8 (a warp scans 8 levels).
 __host__ __device__ constexpr int cluster_for(int nlev) {
   return nlev == 72 ? CAAR_CL72 : nlev == 128 ? CAAR_CL128
          : (nlev >= 8 && nlev <= 64 && nlev % 8 == 0) ? 1
          : nlev == 80 ? 2 : nlev == 96 ? 3 : nlev == 112 ? 2 : nlev == 120 ? 3 : 0;
 }
+// The instance that serves a run-time level count: the smallest compiled level count >= nlev (0 = none: nlev > 128).
+// The levels [nlev, instance) of the column are padding: their threads hold dp = 1, v = 0 and zero-filled tiles, so
+// that every scan contribution from them is exactly 0, and their rows are neither read from nor written to HBM.
+__host__ __device__ constexpr int instance_for(int nlev) {
+  return nlev < 2 ? 0 : nlev <= 64 ? ((nlev + 7) / 8) * 8 : nlev <= 72 ? 72 : nlev <= 80 ? 80 : nlev <= 96 ? 96
+         : nlev <= 112 ? 112 : nlev <= 120 ? 120 : nlev <= 128 ? 128 : 0;
+}
 
 // register budget per thread for a CTA of `threads` threads
 constexpr int regs_for(int threads, bool eul = false) {
-  return (eul && threads > 256 && CAAR_EUL_REGS > 0) ? CAAR_EUL_REGS  // CL = 1 Eulerian: one 288-thread CTA per SM
+  return (eul && threads > 256 && threads <= 320 && CAAR_EUL_REGS > 0) ? CAAR_EUL_REGS  // CL = 1 Eulerian nlev = 72: one 288-thread CTA per SM
          : threads <= 256 ? 128              // cluster CTAs: 5 x 96 or 2 x 256 threads x 128 registers per SM
          : threads <= 320 ? CAAR_REGS_SMALL  // CL = 1: 2 x 288 threads (nlev = 72)
                           : 128;             // CL = 1: one 512-thread CTA per SM (nlev = 128)
@@ -332,7 +343,7 @@ struct Smem {
 // L = levels of the element, CL = CTAs per element (a thread-block cluster of CL CTAs, each holding L/CL levels).
 // CL = 2 is used for nlev = 128: two 256-thread CTAs at 128 registers instead of one 512-thread CTA, so that two
 // CTAs (of different elements, in different phases) share an SM; the vertical scans exchange their per-warp
-// totals through distributed shared memory and a cluster barrier.
+// totals through distributed shared memory with st.async + mbarrier complete_tx (no cluster barrier on that path).
 // EUL = the Eulerian vertical coordinate (rsplit == 0, F/routine_extracted.F90:227-262,325-334,515-517): after the
 // divergence scan every thread also holds the column total S of div(v dp), hence eta_dot_dpdn at the two interfaces
 // of its level (eta_hi = hybi[k+1]*S - prefix_k, eta_lo = hybi[k]*S - prefix_{k-1}, 0 at the top and the bottom);
@@ -346,7 +357,6 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   constexpr int NW = LC / 8;        // warps per CTA
   constexpr int NWT = L / 8;        // warps per element
   constexpr int LF = LC * PTS;      // doubles per scalar level-field slab of this CTA
-  constexpr int LFE = L * PTS;      // ... of the whole element
   constexpr int GS = 20;  // padded igp stride of the 2x2 tensors in shared memory
   constexpr unsigned FB = LF * sizeof(double);  // bytes of one scalar level-field slab
   static_assert(L % (8 * CL) == 0, "a warp holds 8 levels");
@@ -363,13 +373,15 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   const int lev0 = (int)rank * LC;    // first level of this CTA
   const int ie = A.nets + (int)(blockIdx.x / CL);
   const size_t e = (size_t)ie;
-  const size_t lf = LFE;
+  const int nl = A.nlev;               // levels of the column (<= L; the levels [nl, L) of this instance are padding)
+  const size_t lf = (size_t)nl * PTS;  // doubles per scalar level-field of the whole element
   const int off = lev0 * PTS + t * 4;  // this thread's 4 points inside a scalar level-field of the element
+  const bool live = lev0 + (t >> 2) < nl;  // this thread's level exists
   // this thread's first 16-byte chunk inside a swizzled scalar tile (row = level) / (u,v) tile (row = t/2)
   const uint32_t sw1 = (uint32_t)(t >> 2) * 128u + ((uint32_t)((2 * r) ^ ((t >> 2) & 7)) << 4);
   const uint32_t sw2 = (uint32_t)(t >> 1) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((t >> 1) & 7)) << 4);
-  const int row_nm1 = (ie * A.ntl + A.nm1) * L + lev0, row_np1 = (ie * A.ntl + A.np1) * L + lev0;
-  const int row_e = ie * L + lev0;  // first row of this CTA in the [E][L] arrays
+  // TMA coordinates: (row = level [x2 for (u,v)] inside the slice, slice = element [x time level])
+  const int sl_n0 = ie * A.ntl + A.n0, sl_nm1 = ie * A.ntl + A.nm1, sl_np1 = ie * A.ntl + A.np1;
 
   // ---- kernel entry: one thread starts the TMA prefetch of the late inputs
   if (t == 0) {
@@ -400,26 +412,27 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
   if (CL > 1) cluster_arrive_relaxed();
   if (t == 0) {
     mbar_expect_tx(&S.bar[2], ((A.qn0 != -1 ? 2 : 1) + (EUL ? 2 : 0)) * FB);
-    tma_load(S.Tn0, &M.T, (ie * A.ntl + A.n0) * L + lev0, &S.bar[2]);
-    if (EUL) tma_load(S.vn, &M.v, ((ie * A.ntl + A.n0) * L + lev0) * 2, &S.bar[2]);
-    if (A.qn0 != -1) tma_load(S.Qd, &M.Qdp, ((ie * A.qsize_d + 0) * 2 + A.qn0) * L + lev0, &S.bar[2]);
+    tma_load(S.Tn0, &M.T, lev0, sl_n0, &S.bar[2]);
+    if (EUL) tma_load(S.vn, &M.v, lev0 * 2, sl_n0, &S.bar[2]);
+    if (A.qn0 != -1) tma_load(S.Qd, &M.Qdp, lev0, (ie * A.qsize_d + 0) * 2 + A.qn0, &S.bar[2]);
     mbar_expect_tx(&S.bar[0], 4 * FB);
-    tma_load(S.vn0, &M.vn0, row_e * 2, &S.bar[0]);
-    tma_load(S.dpm, &M.dp3d, row_nm1, &S.bar[0]);
-    tma_load(S.pec, &M.pecnd, row_e, &S.bar[0]);
+    tma_load(S.vn0, &M.vn0, lev0 * 2, ie, &S.bar[0]);
+    tma_load(S.dpm, &M.dp3d, lev0, sl_nm1, &S.bar[0]);
+    tma_load(S.pec, &M.pecnd, lev0, ie, &S.bar[0]);
     mbar_expect_tx(&S.bar[1], 4 * FB);
-    tma_load(S.omp, &M.omega_p, row_e, &S.bar[1]);
-    tma_load(S.Tm1, &M.T, row_nm1, &S.bar[1]);
-    tma_load(S.vm1, &M.v, row_nm1 * 2, &S.bar[1]);
+    tma_load(S.omp, &M.omega_p, lev0, ie, &S.bar[1]);
+    tma_load(S.Tm1, &M.T, lev0, sl_nm1, &S.bar[1]);
+    tma_load(S.vm1, &M.v, lev0 * 2, sl_nm1, &S.bar[1]);
     // pull the early inputs and the geometry of a later element (the one expected to run next on this SM slot) into L2, so
     // that its kernel-start loads see L2 latency instead of DRAM latency
     const int pe = ie + A.pf_dist;
-    if (A.pf_dist > 0 && pe < A.nete) {
+    if (A.pf_dist > 0 && pe < A.nete && lev0 < nl) {
       const size_t pn0 = ((size_t)pe * A.ntl + A.n0) * lf + (size_t)lev0 * PTS;
-      prefetch_l2(A.dp3d + pn0, FB);
-      prefetch_l2(A.v + pn0 * 2, 2 * FB);
-      prefetch_l2(A.T + pn0, FB);
-      if (A.qn0 != -1) prefetch_l2(A.Qdp + (((size_t)pe * A.qsize_d + 0) * 2 + A.qn0) * lf + (size_t)lev0 * PTS, FB);
+      const unsigned PB = (nl - lev0 < LC) ? (unsigned)(nl - lev0) * PTS * sizeof(double) : FB;  // this slab, clipped to the column
+      prefetch_l2(A.dp3d + pn0, PB);
+      prefetch_l2(A.v + pn0 * 2, 2 * PB);
+      prefetch_l2(A.T + pn0, PB);
+      if (A.qn0 != -1) prefetch_l2(A.Qdp + (((size_t)pe * A.qsize_d + 0) * 2 + A.qn0) * lf + (size_t)lev0 * PTS, PB);
       if (rank == 0) {
         prefetch_l2(A.Dinv + (size_t)pe * 64, 512);
         prefetch_l2(A.D + (size_t)pe * 64, 512);
@@ -434,11 +447,16 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
 
   // ---- early inputs straight to registers
   const size_t on0 = (e * A.ntl + A.n0) * lf + off;
-  Row dp = ld_row(A.dp3d + on0);
-  Row v1, v2;
-  ld_row2(A.v + on0 * 2, v1, v2);
-  if (EUL && r == 0)  // this level's derived_eta_dot_dpdn line is read-modify-written after the scans: pull it into L2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.eta_dot_dpdn + e * (size_t)(L + 1) * PTS + off));
+  Row dp, v1, v2;
+  if (live) {
+    dp = ld_row(A.dp3d + on0);
+    ld_row2(A.v + on0 * 2, v1, v2);
+  } else {  // padding level: a positive thickness and no wind make every scan contribution of this thread exactly 0
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dp.x[j] = 1.0, v1.x[j] = 0.0, v2.x[j] = 0.0;
+  }
+  if (EUL && r == 0 && live)  // this level's derived_eta_dot_dpdn line is read-modify-written after the scans: pull it into L2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.eta_dot_dpdn + e * (lf + PTS) + off));
 
   // ---- stage the element's geometry
   for (int g = t; g < 96; g += 4 * LC) {  // 96 staging slots; CTAs of fewer threads take several each
@@ -686,8 +704,8 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       if (rank > 0) mbar_wait(&S.xbar[2], 0);
     }
     if (t == 0) {
-      tma_store(&M.vn0, row_e * 2, S.vn0);
-      if (!EUL) tma_store(&M.dp3d, row_np1, S.dpm);
+      tma_store(&M.vn0, lev0 * 2, ie, S.vn0);
+      if (!EUL) tma_store(&M.dp3d, lev0, sl_np1, S.dpm);
       bulk_commit();
     }
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
@@ -746,12 +764,12 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
         }
       }
       const int kg = lev0 + (t >> 2);
-      const double hb_lo = A.hybi[kg], hb_hi = A.hybi[kg + 1];
+      const double hb_lo = A.hybi[kg < nl ? kg : nl], hb_hi = A.hybi[kg < nl ? kg + 1 : nl];
       Row ehi, elo;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double P = cd[j] + divdp.x[j];  // inclusive prefix of div(v dp)
-        ehi.x[j] = (kg == L - 1) ? 0.0 : fma(hb_hi, S4[j], -P);
+        ehi.x[j] = (kg >= nl - 1) ? 0.0 : fma(hb_hi, S4[j], -P);
         elo.x[j] = (kg == 0) ? 0.0 : fma(hb_lo, S4[j], -(P - dsave.x[j]));
       }
       {  // dp3d(np1) = spheremp*(dp3d(nm1) - dt2*(divdp + eta(k+1) - eta(k)))  (F/routine_extracted.F90:515-517)
@@ -760,8 +778,8 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
         for (int j = 0; j < 4; ++j) o.x[j] = mp.x[j] * fma(-A.dt2, (dsave.x[j] + ehi.x[j]) - elo.x[j], o.x[j]);
         st_tile(S.dpm, sw1, o);
       }
-      if (kg > 0) {  // derived_eta_dot_dpdn(k) += eta_ave_w*eta(k) (F:270-277); interfaces 0 and L carry no flux
-        double* pe = A.eta_dot_dpdn + e * (size_t)(L + 1) * PTS + off;
+      if (kg > 0 && live) {  // derived_eta_dot_dpdn(k) += eta_ave_w*eta(k) (F:270-277); interfaces 0 and L carry no flux
+        double* pe = A.eta_dot_dpdn + e * (lf + PTS) + off;
         Row x = ld_row(pe);
 #pragma unroll
         for (int j = 0; j < 4; ++j) x.x[j] = fma(A.eta_ave_w, elo.x[j], x.x[j]);
@@ -770,10 +788,11 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       // preq_vertadv (LV/CaarFunctor.hpp:504-547): fac+ = eta(k+1)/(2 dp), fac- = eta(k)/(2 dp); the one-sided
       // forms at the top and bottom follow from eta = 0 there
       {
-        const Row dpk = ld_row(A.dp3d + on0);  // re-read (L1/L2 hit) rather than 4 doubles live through the scans
+        Row dpk;  // re-read (L1/L2 hit) rather than 4 doubles live through the scans
+        if (live) dpk = ld_row(A.dp3d + on0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const double hr = 0.5 * fast_rcp(dpk.x[j]);
+          const double hr = live ? 0.5 * fast_rcp(dpk.x[j]) : 0.0;
           ehi.x[j] *= hr;
           elo.x[j] *= hr;
         }
@@ -784,7 +803,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       {
         const Row Tk = ld_tile(S.Tn0, sw1);
         Row Tu = Tk, Td = Tk;
-        if (kg + 1 < L) {
+        if (kg + 1 < nl) {
           if (kl + 1 < LC) Tu = ld_tile(S.Tn0, (uint32_t)(kl + 1) * 128u + ((uint32_t)((2 * r) ^ ((kl + 1) & 7)) << 4));
           else Tu = ld_row(A.T + on0 + PTS);
         }
@@ -801,7 +820,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
         ld_tile2(S.vn, sw2, uk, vk);
         uu = uk; vu = vk; ud = uk; vd = vk;
         const int tr = t >> 1;  // this thread's row in the (u,v) tile; a level spans two tile rows
-        if (kg + 1 < L) {
+        if (kg + 1 < nl) {
           if (kl + 1 < LC) ld_tile2(S.vn, (uint32_t)(tr + 2) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((tr + 2) & 7)) << 4), uu, vu);
           else ld_row2(A.v + (on0 + PTS) * 2, uu, vu);
         }
@@ -870,11 +889,11 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     __syncthreads();
   }
   if (t == 0) {
-    if (EUL) tma_store(&M.dp3d, row_np1, S.dpm);
-    tma_store(&M.omega_p, row_e, S.omp);
-    tma_store(&M.T, row_np1, S.Tm1);
-    tma_store(&M.phi, row_e, S.pec);
-    tma_store(&M.v, row_np1 * 2, S.vm1);
+    if (EUL) tma_store(&M.dp3d, lev0, sl_np1, S.dpm);
+    tma_store(&M.omega_p, lev0, ie, S.omp);
+    tma_store(&M.T, lev0, sl_np1, S.Tm1);
+    tma_store(&M.phi, lev0, ie, S.pec);
+    tma_store(&M.v, lev0 * 2, sl_np1, S.vm1);
     bulk_commit();
     bulk_wait_read_all();  // shared memory must stay alive until the TMA engine has read it
   }
@@ -882,6 +901,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
 
 template <int L, int CL, bool EUL>
 cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
+  static_assert((4 * L / CL) * regs_for(4 * L / CL, EUL) <= 65536, "one CTA must fit the 64K-register file of an SM");
   const int n = a.nete - a.nets;
   if (n <= 0) return cudaSuccess;
   constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8, EUL, park_for(L, CL, EUL)>) + 1024;

@@ -1,12 +1,12 @@
 // caar_fused_more.cu — fused kernel instances (caar_fused_kernel.cuh) for the level counts beyond the reference's two
 // configurations: every multiple of 8 up to 64 as one CTA per element, 80 / 96 / 112 / 120 on CTA clusters.
-// (Level counts that are not multiples of 8 run on the reference-order kernel.)
+// Level counts in between run on the next larger instance with padding levels (instance_for()).
 #include "caar_fused_kernel.cuh"
 
 namespace caar {
 
 cudaError_t launch_fused_more(const KernelArgs& a, cudaStream_t s) {
-  switch (a.nlev) {
+  switch (instance_for(a.nlev)) {
     case 8: return launch_nlev<8>(a, s);
     case 16: return launch_nlev<16>(a, s);
     case 24: return launch_nlev<24>(a, s);
