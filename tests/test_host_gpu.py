@@ -59,14 +59,17 @@ def test_driver_cli_errors():
     assert subprocess.run([exe, "--tinman-help"], capture_output=True).returncode == 0
 
 
+@pytest.mark.parametrize("pulls", ["combined", "partial"])
 @pytest.mark.parametrize("mode", ["strict", "fast"])
-def test_hommexx_style_f90_pointer_interface(mode, golden_dir):
-    """host/hommexx_shim.hpp (Control::init, Derivative::init, Elements::init_2d / pull_from_f90_pointers /
-    push_to_f90_pointers — the names and argument order of level_vectorized_ppscan/) driven by a C++ program that
-    hands over Fortran-order arrays: the norms are the reference driver's."""
+def test_hommexx_style_f90_pointer_interface(mode, pulls, golden_dir):
+    """host/hommexx_shim.hpp (the twelve-argument Control::init, Derivative::init, Elements::init_2d /
+    pull_from_f90_pointers / push_to_f90_pointers and the partial pull_* / push_* — the names and argument order of
+    level_vectorized_ppscan/) driven by a C++ program that hands over Fortran-order arrays: the norms are the reference
+    driver's."""
     exe = os.path.join(HOST, "hommexx_shim_test")
     want = _vals(open(os.path.join(golden_dir, "pointers_only_stdout.txt")).read())[3:]     # norms after the run
-    out = subprocess.run([exe, "10", "1", mode], capture_output=True, text=True, check=True).stdout
+    # "partial": pull_3d / pull_4d / pull_eta_dot / pull_qdp and push_* instead of the combined calls
+    out = subprocess.run([exe, "10", "1", mode, pulls], capture_output=True, text=True, check=True).stdout
     got = _vals(out)[:3]
     assert np.max(np.abs(got - want) / want) < 1e-13
     m = re.search(r"= ([0-9.eE+-]+) == Fortran T\(2,3,1,np1\) = ([0-9.eE+-]+)", out)

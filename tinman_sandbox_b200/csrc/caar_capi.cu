@@ -1,6 +1,7 @@
 // caar_capi.cu — the C-ABI of include/caar_b200.h over the CUDA kernels. No CPU fallback: every
 // compute entry point needs a CUDA device and fails with CAAR_ERR_CUDA otherwise.
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,6 +83,16 @@ struct caar_handle_s {
 };
 
 static_assert(sizeof(caar_arrays) == CAAR_NUM_FIELDS * sizeof(double*), "caar_arrays must be 16 pointers");
+// Layouts that include/caar_b200.f90 (bind(C) derived types) and the ctypes binding assume
+static_assert(sizeof(caar_dims) == 20 && offsetof(caar_dims, nlev) == 4 && offsetof(caar_dims, ntl) == 16, "caar_dims: 5 ints");
+static_assert(offsetof(caar_arrays, elem_state_dp3d) == 48 && offsetof(caar_arrays, elem_derived_vn0) == 120,
+              "caar_arrays: the order of struct Arrays");
+static_assert(sizeof(caar_constants) == 48 && offsetof(caar_constants, kappa) == 40, "caar_constants: 6 doubles");
+static_assert(sizeof(caar_control) == 32 && offsetof(caar_control, qn0) == 20 && offsetof(caar_control, dt2) == 24,
+              "caar_control: 6 ints + 1 double");
+static_assert(sizeof(caar_checksum) == 184 && offsetof(caar_checksum, sumsq) == 56 && offsetof(caar_checksum, bits) == 112 &&
+                  offsetof(caar_checksum, energy) == 168,
+              "caar_checksum: 7 + 7 doubles, 7 64-bit integers, 2 doubles");
 
 namespace {
 

@@ -10,6 +10,8 @@
 //   Homme::Elements::pull_from_f90_pointers(state_v, state_t, state_dp3d, derived_phi, derived_pecnd,
 //       derived_omega_p, derived_v, derived_eta_dot_dpdn, state_qdp)    LV/Elements.hpp:99-103, LV/Elements.cpp:154-292
 //   Homme::Elements::push_to_f90_pointers(...same order...)             LV/Elements.hpp:111-115, LV/Elements.cpp:294-435
+//   Homme::Elements::pull_3d / pull_4d / pull_eta_dot / pull_qdp and the push_* counterparts
+//                                                                       LV/Elements.hpp:104-117
 //   Homme::caar(control, elements, derivative)                          = Kokkos::parallel_for(policy, CaarFunctor(...)),
 //                                                                         LV/kokkos_init.cpp:105-131
 //
@@ -40,6 +42,18 @@ struct PhysicalConstants {  // LV/PhysicalConstants.hpp:9-17
   static constexpr Real rrearth = 1.0 / 6.376e6;
 };
 
+// NUM_PHYSICAL_LEV is a compile-time constant of the reference (PLEV, LV/config.h.in:8, LV/Dimensions.hpp:36) and a
+// run-time one here: a process-wide value, PLEV's default unless the caller (or Elements::init) sets another.
+#ifndef PLEV
+#define CAAR_SHIM_DEFAULT_PLEV 72
+#else
+#define CAAR_SHIM_DEFAULT_PLEV PLEV
+#endif
+inline int& num_physical_lev() {
+  static int n = CAAR_SHIM_DEFAULT_PLEV;
+  return n;
+}
+
 namespace detail {
 [[noreturn]] inline void die(const char* what, int rc) {
   std::fprintf(stderr, "hommexx shim: %s failed (code %d): %s\n", what, rc, caar_last_error());
@@ -55,12 +69,14 @@ struct Control {
   int rsplit = 1;  // LV/Control.hpp:47-49: > 0 vertically Lagrangian
   Real dt = 0, eta_ave_w = 0, ps0 = 0;
   std::vector<Real> hybrid_a;
+  // the reference's twelve arguments, in its order (LV/Control.hpp:13-17); hybrid_a has NUM_LEV_P =
+  // num_physical_lev() + 1 entries (LV/Control.cpp:21-26)
   void init(const int nets_in, const int nete_in, const int num_elems_in, const int nm1_in, const int n0_in,
             const int np1_in, const int qn0_in, const Real dt_in, const Real ps0_in, const bool compute_diagonstics_in,
-            const Real eta_ave_w_in, CRCPtr hybrid_a_ptr, const int nlev) {
+            const Real eta_ave_w_in, CRCPtr hybrid_a_ptr) {
     nets = nets_in; nete = nete_in; num_elems = num_elems_in; n0 = n0_in; nm1 = nm1_in; np1 = np1_in; qn0 = qn0_in;
     dt = dt_in; ps0 = ps0_in; compute_diagonstics = compute_diagonstics_in; eta_ave_w = eta_ave_w_in;
-    hybrid_a.assign(hybrid_a_ptr, hybrid_a_ptr + nlev + 1);
+    hybrid_a.assign(hybrid_a_ptr, hybrid_a_ptr + num_physical_lev() + 1);
   }
 };
 
@@ -83,7 +99,9 @@ class Elements {
     if (m_h) caar_destroy(m_h);
   }
   // nlev, qsize_d, timelevels are compile-time in the reference (LV/config.h.in) and run-time here
-  void init(const int num_elems, const int nlev = 72, const int qsize_d = 1, const int timelevels = 3, const int device = 0) {
+  void init(const int num_elems, const int nlev = num_physical_lev(), const int qsize_d = 1, const int timelevels = 3,
+            const int device = 0) {
+    num_physical_lev() = nlev;
     m_dims = caar_dims{num_elems, nlev, CAAR_NP, qsize_d, timelevels};
     detail::ok("caar_create", caar_create(&m_h, &m_dims, device));
   }
@@ -111,6 +129,44 @@ class Elements {
     detail::ok("caar_upload_layout", caar_upload_layout(m_h, &a, k3d4d, CAAR_LAYOUT_F90));
   }
 
+  // the four partial pulls / pushes the combined calls are made of (LV/Elements.hpp:104-117, LV/Elements.cpp:163-292,
+  // 303-435): same names, same argument order
+  void pull_3d(CF90Ptr& derived_phi, CF90Ptr& derived_pecnd, CF90Ptr& derived_omega_p, CF90Ptr& derived_v) {
+    caar_arrays a = view(nullptr, nullptr, nullptr, const_cast<Real*>(derived_phi), const_cast<Real*>(derived_pecnd),
+                         const_cast<Real*>(derived_omega_p), const_cast<Real*>(derived_v), nullptr, nullptr);
+    detail::ok("caar_upload_layout", caar_upload_layout(m_h, &a, k3d, CAAR_LAYOUT_F90));
+  }
+  void pull_4d(CF90Ptr& state_v, CF90Ptr& state_t, CF90Ptr& state_dp3d) {
+    caar_arrays a = view(const_cast<Real*>(state_v), const_cast<Real*>(state_t), const_cast<Real*>(state_dp3d), nullptr,
+                         nullptr, nullptr, nullptr, nullptr, nullptr);
+    detail::ok("caar_upload_layout", caar_upload_layout(m_h, &a, k4d, CAAR_LAYOUT_F90));
+  }
+  void pull_eta_dot(CF90Ptr& derived_eta_dot_dpdn) {
+    caar_arrays a = view(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         const_cast<Real*>(derived_eta_dot_dpdn), nullptr);
+    detail::ok("caar_upload_layout", caar_upload_layout(m_h, &a, CAAR_F_ETA_DOT_DPDN, CAAR_LAYOUT_F90));
+  }
+  void pull_qdp(CF90Ptr& state_qdp) {
+    caar_arrays a = view(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, const_cast<Real*>(state_qdp));
+    detail::ok("caar_upload_layout", caar_upload_layout(m_h, &a, CAAR_F_QDP, CAAR_LAYOUT_F90));
+  }
+  void push_3d(F90Ptr& derived_phi, F90Ptr& derived_pecnd, F90Ptr& derived_omega_p, F90Ptr& derived_v) const {
+    caar_arrays a = view(nullptr, nullptr, nullptr, derived_phi, derived_pecnd, derived_omega_p, derived_v, nullptr, nullptr);
+    detail::ok("caar_download_layout", caar_download_layout(m_h, &a, k3d, CAAR_LAYOUT_F90));
+  }
+  void push_4d(F90Ptr& state_v, F90Ptr& state_t, F90Ptr& state_dp3d) const {
+    caar_arrays a = view(state_v, state_t, state_dp3d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    detail::ok("caar_download_layout", caar_download_layout(m_h, &a, k4d, CAAR_LAYOUT_F90));
+  }
+  void push_eta_dot(F90Ptr& derived_eta_dot_dpdn) const {
+    caar_arrays a = view(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, derived_eta_dot_dpdn, nullptr);
+    detail::ok("caar_download_layout", caar_download_layout(m_h, &a, CAAR_F_ETA_DOT_DPDN, CAAR_LAYOUT_F90));
+  }
+  void push_qdp(F90Ptr& state_qdp) const {
+    caar_arrays a = view(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, state_qdp);
+    detail::ok("caar_download_layout", caar_download_layout(m_h, &a, CAAR_F_QDP, CAAR_LAYOUT_F90));
+  }
+
   void push_to_f90_pointers(F90Ptr& state_v, F90Ptr& state_t, F90Ptr& state_dp, F90Ptr& derived_phi, F90Ptr& derived_pecnd,
                             F90Ptr& derived_omega_p, F90Ptr& derived_v, F90Ptr& derived_eta_dot_dpdn,
                             F90Ptr& state_qdp) const {
@@ -120,6 +176,8 @@ class Elements {
   }
 
  private:
+  static constexpr unsigned k3d = CAAR_F_PHI | CAAR_F_PECND | CAAR_F_OMEGA_P | CAAR_F_VN0;
+  static constexpr unsigned k4d = CAAR_F_V | CAAR_F_T | CAAR_F_DP3D;
   static constexpr unsigned k3d4d = CAAR_F_V | CAAR_F_T | CAAR_F_DP3D | CAAR_F_PHI | CAAR_F_PECND | CAAR_F_OMEGA_P |
                                     CAAR_F_VN0 | CAAR_F_ETA_DOT_DPDN | CAAR_F_QDP;
   static caar_arrays view(Real* v, Real* t, Real* dp, Real* phi, Real* pecnd, Real* omega_p, Real* dv, Real* eta, Real* qdp) {

@@ -48,19 +48,33 @@ int main(int argc, char** argv) {
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) dvv_f90[j * 4 + i] = d.dvv[i * 4 + j];
 
-  Homme::Control control;
+  Homme::Elements elements;
+  elements.init(E, L);  // also sets Homme::num_physical_lev() (PLEV is compile-time in the reference)
+  Homme::Control control;  // the reference's twelve arguments (LV/Control.hpp:13-17)
   control.init(d.ctl.nets, d.ctl.nete, E, d.ctl.nm1, d.ctl.n0, d.ctl.np1, d.ctl.qn0, d.ctl.dt2, d.ps0, false,
-               d.c.eta_ave_w, d.hyai.data(), L);
+               d.c.eta_ave_w, d.hyai.data());
   Homme::Derivative deriv;
   deriv.init(dvv_f90);
-  Homme::Elements elements;
-  elements.init(E, L);
   elements.init_2d(f[D].data(), f[DINV].data(), f[FCOR].data(), f[MP].data(), f[MET].data(), f[PHIS].data());
-  elements.pull_from_f90_pointers(f[V].data(), f[T].data(), f[DP].data(), f[PHI].data(), f[PEC].data(), f[OM].data(),
-                                  f[VN0].data(), f[ETA].data(), f[QDP].data());
+  if (argc > 4 && std::strcmp(argv[4], "partial") == 0) {  // the four partial pulls instead of the combined one
+    elements.pull_3d(f[PHI].data(), f[PEC].data(), f[OM].data(), f[VN0].data());
+    elements.pull_4d(f[V].data(), f[T].data(), f[DP].data());
+    elements.pull_eta_dot(f[ETA].data());
+    elements.pull_qdp(f[QDP].data());
+  } else {
+    elements.pull_from_f90_pointers(f[V].data(), f[T].data(), f[DP].data(), f[PHI].data(), f[PEC].data(), f[OM].data(),
+                                    f[VN0].data(), f[ETA].data(), f[QDP].data());
+  }
   for (int it = 0; it < nexec; ++it) Homme::caar(control, elements, deriv, mode);
-  elements.push_to_f90_pointers(f[V].data(), f[T].data(), f[DP].data(), f[PHI].data(), f[PEC].data(), f[OM].data(),
-                                f[VN0].data(), f[ETA].data(), f[QDP].data());
+  if (argc > 4 && std::strcmp(argv[4], "partial") == 0) {
+    elements.push_3d(f[PHI].data(), f[PEC].data(), f[OM].data(), f[VN0].data());
+    elements.push_4d(f[V].data(), f[T].data(), f[DP].data());
+    elements.push_eta_dot(f[ETA].data());
+    elements.push_qdp(f[QDP].data());
+  } else {
+    elements.push_to_f90_pointers(f[V].data(), f[T].data(), f[DP].data(), f[PHI].data(), f[PEC].data(), f[OM].data(),
+                                  f[VN0].data(), f[ETA].data(), f[QDP].data());
+  }
 
   // norms of v, T, dp3d at np1 straight from the Fortran-order arrays (a 2-norm does not care about the order)
   const size_t lev_pts = (size_t)L * 16;
