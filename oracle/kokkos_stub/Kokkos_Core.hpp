@@ -59,23 +59,29 @@ struct HostSpace {
   using memory_space = HostSpace;
 };
 
-// per-team / per-thread scratch: a bump allocator over a buffer owned by the team member
+// per-team / per-thread scratch: a bump allocator over a fixed arena shared by every copy of the team member
+// (functors take the member by value: the arena must neither move nor be duplicated)
 class ScratchMemorySpaceStub {
  public:
   using memory_space = ScratchMemorySpaceStub;
-  ScratchMemorySpaceStub() : m_buf(nullptr) {}
-  explicit ScratchMemorySpaceStub(std::vector<char>* buf) : m_buf(buf) {}
+  struct Arena {
+    static constexpr size_t kCapacity = size_t(1) << 20;
+    std::unique_ptr<char[]> mem;
+    size_t used;
+    Arena() : mem(new char[kCapacity]()), used(0) {}
+  };
+  ScratchMemorySpaceStub() {}
+  explicit ScratchMemorySpaceStub(const std::shared_ptr<Arena>& arena) : m_arena(arena) {}
   void* get_shmem(size_t bytes) const {
-    if (!m_buf) Kokkos::abort("scratch space requested from a team member without scratch");
-    const size_t at = (m_buf->size() + 63) & ~size_t(63);
-    m_buf->resize(at + bytes, 0);
-    if (m_buf->capacity() > kCapacity) Kokkos::abort("scratch arena exhausted");
-    return m_buf->data() + at;
+    if (!m_arena) Kokkos::abort("scratch space requested from a team member without scratch");
+    const size_t at = (m_arena->used + 63) & ~size_t(63);
+    if (at + bytes > Arena::kCapacity) Kokkos::abort("scratch arena exhausted");
+    m_arena->used = at + bytes;
+    return m_arena->mem.get() + at;
   }
-  static constexpr size_t kCapacity = size_t(1) << 22;  // reserved up front so that pointers stay valid
 
  private:
-  std::vector<char>* m_buf;
+  std::shared_ptr<Arena> m_arena;
 };
 
 struct Serial {
@@ -458,22 +464,22 @@ namespace Impl {
 
 class SerialTeamMember {
  public:
-  SerialTeamMember(int league_rank, int league_size) : m_league_rank(league_rank), m_league_size(league_size) {
-    m_team_scratch.reserve(ScratchMemorySpaceStub::kCapacity);
-    m_thread_scratch.reserve(ScratchMemorySpaceStub::kCapacity);
-  }
+  SerialTeamMember(int league_rank, int league_size)
+      : m_league_rank(league_rank), m_league_size(league_size),
+        m_team_scratch(std::make_shared<ScratchMemorySpaceStub::Arena>()),
+        m_thread_scratch(std::make_shared<ScratchMemorySpaceStub::Arena>()) {}
   int league_rank() const { return m_league_rank; }
   int league_size() const { return m_league_size; }
   int team_rank() const { return 0; }
   int team_size() const { return 1; }
   void team_barrier() const {}
-  ScratchMemorySpaceStub team_scratch(int) const { return ScratchMemorySpaceStub(&m_team_scratch); }
-  ScratchMemorySpaceStub thread_scratch(int) const { return ScratchMemorySpaceStub(&m_thread_scratch); }
+  ScratchMemorySpaceStub team_scratch(int) const { return ScratchMemorySpaceStub(m_team_scratch); }
+  ScratchMemorySpaceStub thread_scratch(int) const { return ScratchMemorySpaceStub(m_thread_scratch); }
   ScratchMemorySpaceStub team_shmem() const { return team_scratch(0); }
 
  private:
   int m_league_rank, m_league_size;
-  mutable std::vector<char> m_team_scratch, m_thread_scratch;
+  std::shared_ptr<ScratchMemorySpaceStub::Arena> m_team_scratch, m_thread_scratch;
 };
 
 template <class ExecSpace>
