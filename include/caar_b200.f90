@@ -29,7 +29,8 @@ module caar_b200
   integer(c_int), parameter, public :: CAAR_F_MUTATED = 64 + 128 + 256 + 2048 + 4096 + 8192 + 32768
   integer(c_int), parameter, public :: CAAR_X_VSTAR = 0, CAAR_X_QTENS = 1, CAAR_X_TENSORVISC = 2, CAAR_X_SCALAR_IN = 3, &
                                        CAAR_X_SCALAR_OUT = 4
-  integer(c_int), parameter, public :: CAAR_OP_DIVERGENCE_WK = 0, CAAR_OP_LAPLACE_SIMPLE = 1, CAAR_OP_LAPLACE_TENSOR = 2
+  integer(c_int), parameter, public :: CAAR_OP_DIVERGENCE_WK = 0, CAAR_OP_LAPLACE_SIMPLE = 1, CAAR_OP_LAPLACE_TENSOR = 2, &
+                                       CAAR_OP_LAPLACE_TENSOR_REPLACE = 3
 
   ! ---- struct caar_dims (5 x int = 20 bytes)
   type, bind(C), public :: caar_dims

@@ -250,11 +250,30 @@ int caar_timer_stop(caar_handle h, float* ms);
      CAAR_X_VSTAR  vstar [E][L][4][4][2]        (derived%vstar(np,np,2,nlev), F/element_mod.F90:70; input)
      CAAR_X_QTENS  qtens [E][qsize_d][L][4][4]  (buffers.qtens, LV/Elements.hpp:71; output)
    Asynchronous on the handle's stream (caar_sync / caar_extra_download wait). mode as in caar_run. */
-enum { CAAR_X_VSTAR = 0, CAAR_X_QTENS = 1 };
+enum { CAAR_X_VSTAR = 0, CAAR_X_QTENS = 1, CAAR_X_TENSORVISC = 2, CAAR_X_SCALAR_IN = 3, CAAR_X_SCALAR_OUT = 4 };
+#define CAAR_NUM_EXTRA 5
 size_t caar_extra_count(const caar_dims* dims, int which);
 int caar_extra_upload(caar_handle h, int which, const double* host);
 int caar_extra_download(caar_handle h, int which, double* host);
 int caar_euler_step(caar_handle h, int nets, int nete, int qn0, int qsize, double dt, int mode);
+
+/* ---- the weak-form operators behind hyperviscosity ----
+   Level-local like the tracer step, on the same kernel skeleton, in the pointers_only index conventions
+   (HOMMEXX view (igp,jgp) == pointers_only [jgp][igp]); uses the handle's Dinv / spheremp mirrors, Dvv, rrearth and
+   three more handle-owned arrays moved with caar_extra_upload/download:
+     CAAR_X_TENSORVISC  tensorVisc [E][4][4][2][2]  (like elem_D; LV/SphereOperators.hpp:560, input)
+     CAAR_X_SCALAR_IN   scalar field [E][L][4][4]   (input of the laplace operators)
+     CAAR_X_SCALAR_OUT  scalar field [E][L][4][4]   (output of every operator; input AND output of *_REPLACE)
+     CAAR_OP_DIVERGENCE_WK           out = divergence_sphere_wk(CAAR_X_VSTAR)            LV/SphereOperators.hpp:493-535
+     CAAR_OP_LAPLACE_SIMPLE          out = divergence_sphere_wk(gradient_sphere(in))     LV/SphereOperators.hpp:537-553
+     CAAR_OP_LAPLACE_TENSOR          out = divergence_sphere_wk(tensorVisc.gradient_sphere(in))   :555-599
+     CAAR_OP_LAPLACE_TENSOR_REPLACE  the same with in == out (CAAR_X_SCALAR_OUT)                   :601-636
+   (the reference's accumulator `Scalar dd;` at :521 is zero-initialised by the vendored Vector's default constructor,
+   LV/vector/KokkosKernels_Vector_SIMD.hpp:32-37: the sum starts from 0.) CAAR_MODE_STRICT is bit-identical to the
+   reference's own code (which the tests run under a serial Kokkos stand-in), CAAR_MODE_FAST within 1e-12 of the field maximum.
+   Asynchronous on the handle's stream. */
+enum { CAAR_OP_DIVERGENCE_WK = 0, CAAR_OP_LAPLACE_SIMPLE = 1, CAAR_OP_LAPLACE_TENSOR = 2, CAAR_OP_LAPLACE_TENSOR_REPLACE = 3 };
+int caar_sphere_wk(caar_handle h, int op, int nets, int nete, int mode);
 
 /* Sum of squares of v, T, dp3d at time level `tl` over elements [nets,nete) — the three quantities
    print_results_2norm takes the sqrt of (PO/compute_and_apply_rhs.cpp:384-398). Returned as SUMS OF

@@ -365,10 +365,12 @@ def test_leapfrog_stepping_with_time_level_rotation(mode):
 
 
 @pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
-@pytest.mark.parametrize("nlev,qsize_d,qsize,qn0", [(72, 1, 1, 0), (72, 4, 3, 1), (128, 2, 2, 0), (20, 5, 5, 1)])
+@pytest.mark.parametrize("nlev,qsize_d,qsize,qn0", [(72, 1, 1, 0), (72, 4, 3, 1), (128, 2, 2, 0), (20, 5, 5, 1), (30, 3, 3, 0),
+                                                    (26, 2, 1, 1), (72, 35, 35, 0), (100, 2, 2, 1), (37, 1, 1, 0)])
 def test_euler_step_tracer_rhs(mode, nlev, qsize_d, qsize, qn0):
-    """qtens = Qdp(qn0) - dt*divergence_sphere(vstar*Qdp(qn0)) against the CPU restatement
-    (operator pinned to the reference's divergence_sphere in tests/test_oracle.py). Strict mode bit-exact."""
+    """qtens = Qdp(qn0) - dt*divergence_sphere(vstar*Qdp(qn0)) against the CPU restatement, which is
+    pinned to the reference's own divergence_sphere_update (tests/test_oracle_hommexx.py). Strict mode bit-exact. Level
+    counts that do not fill whole slabs / warps and the reference's QSIZE_D = 35 (LV/config.h.in:10) included."""
     orc = harness.PortOracle()
     s = harness.randomize(orc.init(9, nlev, qsize_d), seed=31 + nlev)
     s.ctl[0:2] = (1, 8)
@@ -635,3 +637,68 @@ def test_set_stream_orders_against_the_previous_stream():
     h.download(got.arrays, names=None)
     h.close()
     check(got, want, exact=True)
+
+
+@pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
+@pytest.mark.parametrize("nlev", [72, 128, 30, 26, 100, 5])
+def test_weak_form_operators(mode, nlev):
+    """SURVEY §8f rank 4, the hyperviscosity half: divergence_sphere_wk, laplace_simple, laplace_tensor and
+    laplace_tensor_replace (LV/SphereOperators.hpp:493-636) through caar_sphere_wk against the CPU restatement, which is
+    bit-identical to the reference's own code run under the Kokkos stand-in (tests/test_oracle_hommexx.py). Strict mode
+    bit-exact, fast mode 1e-12 of the field maximum; a sub-range of elements leaves the rest of the output alone."""
+    orc = harness.PortOracle()
+    E = 9
+    s = harness.randomize(orc.init(E, nlev), seed=nlev + 50)
+    rng = np.random.default_rng(nlev)
+    vin = rng.uniform(-40.0, 40.0, size=(E, nlev, 4, 4, 2))
+    sin = rng.uniform(200.0, 300.0, size=(E, nlev, 4, 4))
+    tv = rng.uniform(-1.0, 1.0, size=(E, 4, 4, 2, 2))
+    h = tb.Caar(E, nlev)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.upload(s.arrays)
+    h.upload_extra(tb.X_VSTAR, vin)
+    h.upload_extra(tb.X_SCALAR_IN, sin)
+    h.upload_extra(tb.X_TENSORVISC, tv)
+    sentinel = np.full((E, nlev, 4, 4), -7.0)
+    for op, name, field in ((tb.OP_DIVERGENCE_WK, "divergence_sphere_wk", vin), (tb.OP_LAPLACE_SIMPLE, "laplace_simple", sin),
+                            (tb.OP_LAPLACE_TENSOR, "laplace_tensor", sin)):
+        want = orc.sphere_wk(name, s, field, tv if name == "laplace_tensor" else None)
+        h.upload_extra(tb.X_SCALAR_OUT, sentinel)
+        h.sphere_wk(op, mode, nets=1, nete=E - 2)
+        got = h.download_extra(tb.X_SCALAR_OUT, (E, nlev, 4, 4))
+        assert np.all(got[0] == -7.0) and np.all(got[E - 2:] == -7.0), name
+        if mode == tb.MODE_STRICT:
+            assert np.array_equal(got[1:E - 2], want[1:E - 2]), name
+        else:
+            assert rel_err(got[1:E - 2], want[1:E - 2]) <= TOL, (name, rel_err(got[1:E - 2], want[1:E - 2]))
+    want = orc.sphere_wk("laplace_tensor", s, sin, tv)
+    h.upload_extra(tb.X_SCALAR_OUT, sin)
+    h.sphere_wk(tb.OP_LAPLACE_TENSOR_REPLACE, mode, nets=0, nete=E)
+    got = h.download_extra(tb.X_SCALAR_OUT, (E, nlev, 4, 4))
+    h.close()
+    if mode == tb.MODE_STRICT:
+        assert np.array_equal(got, want)
+    else:
+        assert rel_err(got, want) <= TOL
+
+
+def test_biharmonic_is_two_laplacians():
+    """A property the composition offers at any size: laplace_simple applied twice through the in-place form equals the
+    oracle's two applications (the hyperviscosity operator is nabla^4), ne=30-sized."""
+    orc = harness.PortOracle()
+    E, L = 600, 72
+    s = harness.randomize(orc.init(E, L), seed=77)
+    sin = np.random.default_rng(1).uniform(200.0, 300.0, size=(E, L, 4, 4))
+    ones = np.zeros((E, 4, 4, 2, 2))
+    ones[..., 0, 0] = ones[..., 1, 1] = 1.0                      # tensorVisc = identity: laplace_tensor == laplace_simple
+    want = orc.sphere_wk("laplace_simple", s, orc.sphere_wk("laplace_simple", s, sin))
+    h = tb.Caar(E, L)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.upload(s.arrays)
+    h.upload_extra(tb.X_TENSORVISC, ones)
+    h.upload_extra(tb.X_SCALAR_OUT, sin)
+    h.sphere_wk(tb.OP_LAPLACE_TENSOR_REPLACE, tb.MODE_FAST)
+    h.sphere_wk(tb.OP_LAPLACE_TENSOR_REPLACE, tb.MODE_FAST)
+    got = h.download_extra(tb.X_SCALAR_OUT, (E, L, 4, 4))
+    h.close()
+    assert rel_err(got, want) <= 2 * TOL

@@ -27,7 +27,8 @@ F_ALL = 0xFFFF
 F_MUTATED = sum(FIELD_BIT[n] for n in MUTATED_FIELDS)
 MODE_FAST, MODE_STRICT = 0, 1
 LAYOUT_CXX, LAYOUT_F90 = 0, 1
-X_VSTAR, X_QTENS = 0, 1
+X_VSTAR, X_QTENS, X_TENSORVISC, X_SCALAR_IN, X_SCALAR_OUT = 0, 1, 2, 3, 4
+OP_DIVERGENCE_WK, OP_LAPLACE_SIMPLE, OP_LAPLACE_TENSOR, OP_LAPLACE_TENSOR_REPLACE = 0, 1, 2, 3
 
 # every symbol include/caar_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -39,6 +40,7 @@ EXPORTED_SYMBOLS = (
     "caar_sync", "caar_launch_count", "caar_timer_start",
     "caar_timer_stop", "caar_norms", "caar_compute_and_apply_rhs_host", "caar_saxpby_device",
     "caar_saxpby_host", "caar_checksums", "caar_upload_range", "caar_download_range", "caar_describe",
+    "caar_sphere_wk",
 )
 CHECKSUM_FIELDS = ("elem_state_dp3d", "elem_state_v", "elem_state_T", "elem_derived_eta_dot_dpdn",
                    "elem_derived_omega_p", "elem_derived_phi", "elem_derived_vn0")
@@ -130,6 +132,7 @@ def load_library():
     lib.caar_extra_count.argtypes = [C.POINTER(Dims), C.c_int]
     lib.caar_extra_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     lib.caar_extra_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    lib.caar_sphere_wk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.caar_euler_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
     lib.caar_upload_layout.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int]
     lib.caar_download_layout.argtypes = [C.c_void_p, C.POINTER(Arrays), C.c_uint, C.c_int]
@@ -358,6 +361,29 @@ class Caar:
             raise CaarError("qtens: need a C-contiguous float64 array [E][qsize_d][L][4][4]")
         _check(self.lib, self.lib.caar_extra_download(self.h, X_QTENS, _dp(qtens)), "caar_extra_download")
         return qtens
+
+    # -- the weak-form operators behind hyperviscosity (LV/SphereOperators.hpp:493-636) ---------------------
+    def upload_extra(self, which, a):
+        n = int(self.lib.caar_extra_count(C.byref(self.dims), which))
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.size != n:
+            raise CaarError(f"extra array {which}: need a C-contiguous float64 array of {n} values")
+        _check(self.lib, self.lib.caar_extra_upload(self.h, which, _dp(a)), "caar_extra_upload")
+
+    def download_extra(self, which, shape):
+        a = np.zeros(shape)
+        if a.size != int(self.lib.caar_extra_count(C.byref(self.dims), which)):
+            raise CaarError(f"extra array {which}: wrong shape {shape}")
+        _check(self.lib, self.lib.caar_extra_download(self.h, which, _dp(a)), "caar_extra_download")
+        return a
+
+    def sphere_wk(self, op, mode=MODE_FAST, nets=None, nete=None, sync=True):
+        """caar_sphere_wk: OP_DIVERGENCE_WK (of X_VSTAR), OP_LAPLACE_SIMPLE / OP_LAPLACE_TENSOR (of X_SCALAR_IN),
+        OP_LAPLACE_TENSOR_REPLACE (X_SCALAR_OUT in place) -> X_SCALAR_OUT."""
+        nets = self.control.nets if nets is None else nets
+        nete = self.control.nete if nete is None else nete
+        _check(self.lib, self.lib.caar_sphere_wk(self.h, int(op), nets, nete, mode), "caar_sphere_wk")
+        if sync:
+            self.sync()
 
     def compute_and_apply_rhs_host(self, arrays: dict, mode=MODE_FAST, chunk_elems=0):
         """Homme::compute_and_apply_rhs(TestData&) on HOST arrays (PO/main.cpp:113-121 calls it this way):

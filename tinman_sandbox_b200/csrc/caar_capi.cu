@@ -76,7 +76,7 @@ struct caar_handle_s {
   // caar_run_host zero-copy path: TMA descriptors over the caller's mapped host arrays, rebuilt when they move
   int rsplit;        // > 0 vertically Lagrangian (default 1), 0 Eulerian
   double* hybi_dev;  // [nlev+1], Eulerian branch only
-  double* extra[2];  // tracer-step arrays beyond struct Arrays: vstar, qtens (allocated on first use)
+  double* extra[5];  // arrays beyond struct Arrays: vstar, qtens, tensorVisc, scalar in / out (allocated on first use)
   double* stage;  // device staging buffer of the Fortran-layout copies (allocated on first use)
   caar::TmaMaps* tma_host;
   double* tma_host_key[CAAR_NUM_FIELDS];
@@ -252,7 +252,7 @@ int caar_destroy(caar_handle h) {
   if (h->bits) cudaFree(h->bits);
   if (h->out3) cudaFree(h->out3);
   if (h->stage) cudaFree(h->stage);
-  for (int x = 0; x < 2; ++x)
+  for (int x = 0; x < CAAR_NUM_EXTRA; ++x)
     if (h->extra[x]) cudaFree(h->extra[x]);
   if (h->hybi_dev) cudaFree(h->hybi_dev);
   if (h->out3_host) cudaFreeHost(h->out3_host);
@@ -705,12 +705,14 @@ size_t caar_extra_count(const caar_dims* d, int which) {
   if (!d) return 0;
   if (which == CAAR_X_VSTAR) return (size_t)d->nelem * d->nlev * 32;
   if (which == CAAR_X_QTENS) return (size_t)d->nelem * d->qsize_d * d->nlev * 16;
+  if (which == CAAR_X_TENSORVISC) return (size_t)d->nelem * 64;
+  if (which == CAAR_X_SCALAR_IN || which == CAAR_X_SCALAR_OUT) return (size_t)d->nelem * d->nlev * 16;
   return 0;
 }
 
 static int extra_buffer(caar_handle h, int which, double** out) {
   if (!h) return fail(CAAR_ERR_INVALID, "null handle");
-  if (which != CAAR_X_VSTAR && which != CAAR_X_QTENS) return fail(CAAR_ERR_INVALID, "extra array %d", which);
+  if (which < 0 || which >= CAAR_NUM_EXTRA) return fail(CAAR_ERR_INVALID, "extra array %d", which);
   if (!h->extra[which]) {
     const size_t bytes = caar_extra_count(&h->dims, which) * sizeof(double);
     CU_TRY(cudaMalloc(&h->extra[which], bytes));
@@ -754,8 +756,40 @@ int caar_euler_step(caar_handle h, int nets, int nete, int qn0, int qsize, doubl
   if (int rc = extra_buffer(h, CAAR_X_VSTAR, &vstar)) return rc;
   if (int rc = extra_buffer(h, CAAR_X_QTENS, &qtens)) return rc;
   const caar::KernelArgs a = make_args(h, nullptr);
-  CU_TRY(caar::launch_euler_step(a, vstar, qtens, nets, nete, qn0, qsize, dt, mode == CAAR_MODE_STRICT, h->stream));
+  // fast mode: the TMA-pipelined level-local skeleton (caar_levelops.cu); CAAR_EULER_V1=1 keeps the first-generation
+  // LDG/STG kernel for A/B runs. Strict mode: the reference-order kernel of caar_euler.cu.
+  static const bool v1 = [] { const char* e = getenv("CAAR_EULER_V1"); return e && atoi(e) != 0; }();
+  if (mode == CAAR_MODE_STRICT || v1)
+    CU_TRY(caar::launch_euler_step(a, vstar, qtens, nets, nete, qn0, qsize, dt, mode == CAAR_MODE_STRICT, h->stream));
+  else
+    CU_TRY(caar::launch_levelop(0, a, a.Qdp, vstar, qtens, nullptr, nets, nete, qn0, qsize, dt, false, h->stream));
   if (nete > nets && qsize > 0) ++h->launches;
+  return CAAR_OK;
+}
+
+int caar_sphere_wk(caar_handle h, int op, int nets, int nete, int mode) {
+  if (!h) return fail(CAAR_ERR_INVALID, "null handle");
+  if (!h->params_set) return fail(CAAR_ERR_STATE, "caar_set_params must be called before caar_sphere_wk");
+  if (nets < 0 || nete > h->dims.nelem || nets > nete) return fail(CAAR_ERR_INVALID, "element range [%d,%d)", nets, nete);
+  if (op < CAAR_OP_DIVERGENCE_WK || op > CAAR_OP_LAPLACE_TENSOR_REPLACE) return fail(CAAR_ERR_INVALID, "op=%d", op);
+  if (mode != CAAR_MODE_FAST && mode != CAAR_MODE_STRICT) return fail(CAAR_ERR_INVALID, "mode=%d", mode);
+  DeviceGuard guard(h->device);
+  double *vin = nullptr, *sin = nullptr, *out = nullptr, *tv = nullptr;
+  if (int rc = extra_buffer(h, CAAR_X_SCALAR_OUT, &out)) return rc;
+  if (op == CAAR_OP_DIVERGENCE_WK) {
+    if (int rc = extra_buffer(h, CAAR_X_VSTAR, &vin)) return rc;
+  } else if (op == CAAR_OP_LAPLACE_TENSOR_REPLACE) {
+    sin = out;
+  } else {
+    if (int rc = extra_buffer(h, CAAR_X_SCALAR_IN, &sin)) return rc;
+  }
+  if (op == CAAR_OP_LAPLACE_TENSOR || op == CAAR_OP_LAPLACE_TENSOR_REPLACE)
+    if (int rc = extra_buffer(h, CAAR_X_TENSORVISC, &tv)) return rc;
+  const caar::KernelArgs a = make_args(h, nullptr);
+  const int kop = op == CAAR_OP_DIVERGENCE_WK ? 1 : op == CAAR_OP_LAPLACE_SIMPLE ? 2 : 3;
+  CU_TRY(caar::launch_levelop(kop, a, kop == 1 ? vin : sin, nullptr, out, tv, nets, nete, 0, 1, 0.0,
+                              mode == CAAR_MODE_STRICT, h->stream));
+  if (nete > nets) ++h->launches;
   return CAAR_OK;
 }
 

@@ -80,6 +80,11 @@ cudaError_t launch_reciprocal(double* out, const double* in, size_t n, cudaStrea
 // tracer step after CAAR (caar_euler.cu): qtens = Qdp(qn0) - dt*divergence_sphere(vstar*Qdp(qn0))
 cudaError_t launch_euler_step(const KernelArgs& a, const double* vstar, double* qtens, int nets, int nete, int qn0,
                               int qsize, double dt, bool strict, cudaStream_t s);
+// level-local operators on the TMA-pipelined skeleton (caar_levelops.cu): op 0 tracer step, 1 divergence_sphere_wk,
+// 2 laplace_simple, 3 laplace_tensor
+cudaError_t launch_levelop(int op, const KernelArgs& k, const double* in, const double* item, double* out,
+                           const double* tensorvisc, int nets, int nete, int qn0, int qsize, double dt, bool strict,
+                           cudaStream_t s);
 cudaError_t launch_saxpby(double a, double b, double* x, const double* y, size_t n, cudaStream_t s);
 // checksums of the seven mutated arrays + energy norms (caar_aux.cu); partial [nelem][8][2], bits [nelem][7]
 cudaError_t launch_checksums(const KernelArgs& a, int tl, int nets, int nete, double cp, double* partial,

@@ -905,13 +905,20 @@ cudaError_t launch_L(const KernelArgs& a, cudaStream_t s) {
   const int n = a.nete - a.nets;
   if (n <= 0) return cudaSuccess;
   constexpr int SMEM = (int)sizeof(Smem<L / CL, L / 8, EUL, park_for(L, CL, EUL)>) + 1024;
-  // per device (function attributes are per context): cheap enough to set on every launch
-  cudaError_t e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  // function attributes are per device: set once per (instance, device), not on every launch
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  // ask for the largest shared-memory carveout so that two ~80 KB CTAs are resident per SM
-  e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           (int)cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    // ask for the largest shared-memory carveout so that several ~30-80 KB CTAs are resident per SM
+    e = cudaFuncSetAttribute(caar_fused_kernel<L, CL, EUL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
   if (!a.tma) return cudaErrorInvalidValue;
   static const bool debug_occ = getenv("CAAR_DEBUG_OCC") != nullptr;
   if (debug_occ) {

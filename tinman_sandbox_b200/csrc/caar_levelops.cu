@@ -1,0 +1,466 @@
+// caar_levelops.cu — the level-local operators around compute_and_apply_rhs on ONE skeleton:
+//
+//   OP_EULER           qtens[e][iq][k] = Qdp[e][iq][qn0][k] - dt * divergence_sphere(vstar[e][k] * Qdp[e][iq][qn0][k])
+//                      EulerStepFunctor::operator() = divergence_sphere_update(alpha = -dt, beta = 1)
+//                      (level_vectorized_ppscan/EulerStepFunctor.hpp:33-66, SphereOperators.hpp:362-403)
+//   OP_DIVERGENCE_WK   out[e][k] = divergence_sphere_wk(vin[e][k])                  (SphereOperators.hpp:493-535)
+//   OP_LAPLACE_SIMPLE  out[e][k] = divergence_sphere_wk(gradient_sphere(sin[e][k])) (SphereOperators.hpp:537-553)
+//   OP_LAPLACE_TENSOR  out[e][k] = divergence_sphere_wk(tensorVisc[e] . gradient_sphere(sin[e][k]))
+//                      (SphereOperators.hpp:555-636; "replace" = the same in place)
+//
+// in the pointers_only array conventions ([e]...[lev][igp][jgp]([c])). Levels are independent here (no vertical
+// integral), so the unit of work is one group of 8 levels of one element for one streamed field = one WARP: lane = (level
+// of the group, GLL row), 4 points each, as in the fused CAAR kernel.
+//
+// Data movement — the fused kernel's: every level-field array is a 3-D TMA tensor [slice][level][16 doubles]; the
+// streamed input tiles (Qdp / vin / sin; 8 levels = 1 KB = one 128-byte-swizzle atom) arrive through an NS-deep ring of
+// shared-memory stages PER WARP, filled by the warp's lane 0 with cp.async.bulk.tensor (UTMALDG) completing on the warp's
+// own mbarriers, NS tiles ahead of the math; results leave as bulk tensor stores (UTMASTG) from a 2-deep ring of output
+// tiles; vstar (OP_EULER) is a per-(element, group) tile, double-buffered and fetched two items ahead. Every warp of the
+// persistent grid is an independent pipeline (__syncwarp only — the first version synchronised whole CTAs per tile and was
+// latency-bound at 0.3-0.6 of the peak) over a contiguous range of the unit list (element, group, tracer), tracer
+// fastest: the row's geometry is loaded once per element, the flux weights once per (element, group). Rows of a group
+// beyond nlev are zero-filled on load and clipped on store: any nlev works.
+//
+// OP_EULER fast path per tracer and thread: the 16 values of the level's Qdp tile (8 conflict-free LDS.128 — the four
+// threads of a level read the same 16 bytes) against 16 + 8 coefficients held in registers,
+//   out(r,j) = q(r,j) + sum_m A(m,j) q(m,j) + c(r,j) sum_m Dvv[m][j] w2(r,m) q(r,m),
+//   c(r,j) = -dt rmetdet(r,j) rrearth,  A(m,j) = c(r,j) Dvv[m][r] w1(m,j),  (w1,w2) = metdet Dinv vstar
+//   — no shuffles and no geometry loads inside the tracer loop.
+// The weak-form operators use the fused kernel's row decomposition: sums along jgp thread-local, sums along igp through
+// three xor-shuffles per value.
+//
+// Bound: HBM. Algorithmic bytes per element*level(*tracer): OP_EULER 256 + (256 + 1408/L)/qsize; OP_DIVERGENCE_WK
+// 384 + 640/L; OP_LAPLACE_* 256 + (640 | 1152)/L.
+//
+// CAAR_MODE_STRICT: reference operation order with __dmul_rn/__dadd_rn (bit-identical to the CPU restatement, which is
+// bit-identical to the reference's own HOMMEXX code for the weak-form operators): plain point-per-thread kernels below;
+// the tracer step's strict variant stays in caar_euler.cu.
+#include "caar_fused_kernel.cuh"
+
+namespace caar {
+namespace {
+
+constexpr int NS = 4;   // input tiles in flight per warp
+constexpr int NO = 2;   // output tiles in flight per warp
+constexpr int WPC = 4;  // warps per CTA (independent pipelines: no CTA-wide barrier after the prologue)
+constexpr int GL = 8;   // levels per tile = levels per warp (8 levels x 4 GLL rows = 32 lanes)
+
+struct LevelOpArgs {
+  const double* Dinv;
+  const double* metdet;
+  const double* rmetdet;
+  const double* spheremp;
+  const double* tensorvisc;
+  int nlev, nets, ngroups, Q, qn0, qsize_d;
+  long long units;  // elements * ngroups * Q
+  double dt, rrearth;
+  double dvv[16];
+};
+struct alignas(64) LevelOpMaps {
+  CUtensorMap in, out, item;
+};
+
+// c[m] = Dvv[m][r] / c[m] = Dvv[r][m] without dynamic indexing of the kernel parameters
+__device__ __forceinline__ void dvv_col(const double* __restrict__ dvv, int r, double (&c)[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double x = dvv[m * 4 + 0];
+    if (r == 1) x = dvv[m * 4 + 1];
+    if (r == 2) x = dvv[m * 4 + 2];
+    if (r == 3) x = dvv[m * 4 + 3];
+    c[m] = x;
+  }
+}
+__device__ __forceinline__ void dvv_row(const double* __restrict__ dvv, int r, double (&c)[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double x = dvv[0 * 4 + m];
+    if (r == 1) x = dvv[1 * 4 + m];
+    if (r == 2) x = dvv[2 * 4 + m];
+    if (r == 3) x = dvv[3 * 4 + m];
+    c[m] = x;
+  }
+}
+
+enum { OP_EULER = 0, OP_DIVWK = 1, OP_LAP_SIMPLE = 2, OP_LAP_TENSOR = 3 };
+
+// Every WARP is an independent pipeline over a contiguous range of units (element, group of 8 levels, tracer), tracer
+// fastest: its lane 0 issues the TMA loads NS tiles ahead and the TMA stores, the warp waits on its own mbarriers and
+// synchronises with __syncwarp only.
+template <int OP>
+__global__ void __launch_bounds__(32 * WPC, 4) levelop_kernel(const __grid_constant__ LevelOpArgs A,
+                                                              const __grid_constant__ LevelOpMaps M) {
+  constexpr unsigned IN_B = (OP == OP_DIVWK) ? 2048u : 1024u;  // bytes of a streamed input tile (8 levels)
+  constexpr unsigned OUT_B = 1024u, ITEM_B = (OP == OP_EULER) ? 2048u : 0u;
+  constexpr unsigned WARP_B = NS * IN_B + NO * OUT_B + 2 * ITEM_B;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31, r = lane & 3, lvl = lane >> 2;
+  unsigned char* in_tiles = base + w * WARP_B;
+  unsigned char* out_tiles = in_tiles + NS * IN_B;
+  unsigned char* item_tiles = out_tiles + NO * OUT_B;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + WPC * WARP_B) + w * (NS + 2);  // [NS] input stages, [2] item tiles
+  uint64_t* item_full = full + NS;
+
+  const int Q = A.Q;
+  const long long wid = (long long)blockIdx.x * WPC + w, nwarps = (long long)gridDim.x * WPC;
+  const long long u0 = A.units * wid / nwarps, u1 = A.units * (wid + 1) / nwarps;
+  const int n = (int)(u1 - u0);
+  if (n <= 0) return;  // whole warp
+
+  // swizzled offsets of this lane's data inside a scalar tile (row = level) and a (u,v) tile (row = 2*level + r/2)
+  const uint32_t sw1 = (uint32_t)lvl * 128u + ((uint32_t)((2 * r) ^ (lvl & 7)) << 4);
+  const uint32_t sw2 = (uint32_t)(lane >> 1) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((lane >> 1) & 7)) << 4);
+
+  auto issue_in = [&](int i) {  // unit i of this warp -> stage i % NS (lane 0 only)
+    const long long u = u0 + i;
+    const long long item = u / Q;
+    const int iq = (int)(u - item * Q);
+    const int e = A.nets + (int)(item / A.ngroups), lev0 = (int)(item % A.ngroups) * GL;
+    const int s = i % NS;
+    mbar_expect_tx(&full[s], IN_B);
+    if (OP == OP_EULER) tma_load(in_tiles + s * IN_B, &M.in, lev0, (e * A.qsize_d + iq) * 2 + A.qn0, &full[s]);
+    else if (OP == OP_DIVWK) tma_load(in_tiles + s * IN_B, &M.in, lev0 * 2, e, &full[s]);
+    else tma_load(in_tiles + s * IN_B, &M.in, lev0, e, &full[s]);
+  };
+  auto issue_item = [&](long long item, int k) {  // vstar of (element, group) -> item buffer k % 2 (lane 0 only)
+    const int e = A.nets + (int)(item / A.ngroups), lev0 = (int)(item % A.ngroups) * GL;
+    mbar_expect_tx(&item_full[k & 1], ITEM_B);
+    tma_load(item_tiles + (k & 1) * ITEM_B, &M.item, lev0 * 2, e, &item_full[k & 1]);
+  };
+
+  const long long item0 = u0 / Q, item_last = (u0 + n - 1) / Q;
+  if (lane == 0) {
+    for (int s = 0; s < NS + 2; ++s) mbar_init(&full[s], 1);
+    fence_proxy_async();
+    for (int i = 0; i < NS && i < n; ++i) issue_in(i);
+    if (OP == OP_EULER) {
+      issue_item(item0, 0);
+      if (item_last > item0) issue_item(item0 + 1, 1);
+    }
+  }
+  __syncwarp();
+
+  double cx[4], cr[4];  // cx[x] = Dvv[r^x][r] (strong form, sum over the first index); cr[x] = Dvv[r][r^x] (weak form)
+  {
+    double col[4], row[4];
+    dvv_col(A.dvv, r, col);
+    dvv_row(A.dvv, r, row);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      double a = col[0 ^ x], b = row[0 ^ x];  // static index per (r, x): select over r
+      if (r == 1) a = col[1 ^ x], b = row[1 ^ x];
+      if (r == 2) a = col[2 ^ x], b = row[2 ^ x];
+      if (r == 3) a = col[3 ^ x], b = row[3 ^ x];
+      cx[x] = a;
+      cr[x] = b;
+    }
+  }
+
+  long long cur_item = -1;
+  int cur_e = -1, item_k = -1;
+  // per-element state: this row's geometry
+  double di[4][4], met[4], rm[4], mp4[4], tv[4][4];
+  // per-item state (OP_EULER): Ac[x][j] = rm[j] Dvv[r^x][r] w1(r^x, j) for row r^x, and this row's w2
+  double Ac[4][4], w2[4];
+  int e = 0, lev0 = 0;
+
+  for (int i = 0; i < n; ++i) {
+    const long long u = u0 + i;
+    const long long item = u / Q;
+    const int iq = (int)(u - item * Q);
+    if (item != cur_item) {  // uniform over the warp
+      cur_item = item;
+      ++item_k;
+      e = A.nets + (int)(item / A.ngroups);
+      lev0 = (int)(item % A.ngroups) * GL;
+      if (e != cur_e) {  // this row's geometry: once per element, reused over its level groups and tracers
+        cur_e = e;
+        const size_t ge = (size_t)e;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4));
+          const double2 b = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4 + 2));
+          di[j][0] = a.x; di[j][1] = a.y; di[j][2] = b.x; di[j][3] = b.y;
+          if (OP == OP_LAP_TENSOR) {
+            const double2 c = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4));
+            const double2 d = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4 + 2));
+            tv[j][0] = c.x; tv[j][1] = c.y; tv[j][2] = d.x; tv[j][3] = d.y;
+          }
+        }
+        if (OP == OP_EULER) {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(A.metdet + ge * 16 + r * 4));
+          const double2 b = __ldg(reinterpret_cast<const double2*>(A.metdet + ge * 16 + r * 4 + 2));
+          met[0] = a.x; met[1] = a.y; met[2] = b.x; met[3] = b.y;
+          const double2 c = __ldg(reinterpret_cast<const double2*>(A.rmetdet + ge * 16 + r * 4));
+          const double2 d = __ldg(reinterpret_cast<const double2*>(A.rmetdet + ge * 16 + r * 4 + 2));
+          const double sc = -A.dt * A.rrearth;  // rm = -dt * rmetdet * rrearth
+          rm[0] = c.x * sc; rm[1] = c.y * sc; rm[2] = d.x * sc; rm[3] = d.y * sc;
+        } else {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4));
+          const double2 b = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4 + 2));
+          mp4[0] = a.x * A.rrearth; mp4[1] = a.y * A.rrearth; mp4[2] = b.x * A.rrearth; mp4[3] = b.y * A.rrearth;
+        }
+      }
+      if (OP == OP_EULER) {
+        mbar_wait(&item_full[item_k & 1], (item_k >> 1) & 1);
+        Row us, vs;
+        ld_tile2(reinterpret_cast<const double*>(item_tiles + (item_k & 1) * ITEM_B), sw2, us, vs);
+        __syncwarp();  // every lane has read the vstar tile: its buffer may be refilled (two items ahead)
+        if (lane == 0 && item + 2 <= item_last) issue_item(item + 2, item_k + 2);
+        double w1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w1[j] = met[j] * fma(di[j][0], us.x[j], di[j][1] * vs.x[j]);
+          w2[j] = met[j] * fma(di[j][2], us.x[j], di[j][3] * vs.x[j]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double wx = x == 0 ? w1[j] : __shfl_xor_sync(FULL, w1[j], x);  // w1(r^x, j)
+            Ac[x][j] = rm[j] * (cx[x] * wx);
+          }
+      }
+    }
+
+    const int s = i % NS;
+    mbar_wait(&full[s], (i / NS) & 1);
+    const unsigned char* tile = in_tiles + s * IN_B;
+    Row out;
+    if (OP == OP_EULER) {
+      Row q[4];  // the level's 16 tracer values: row m = chunks 2m, 2m+1 of the 128-byte tile row
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int m = r ^ x;
+        const uint32_t o = (uint32_t)lvl * 128u + ((uint32_t)((2 * m) ^ (lvl & 7)) << 4);
+        q[x] = ld_tile(reinterpret_cast<const double*>(tile), o);
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NO - 1) : "memory");
+      __syncwarp();  // stage s is consumed by every lane; the output tile i % NO is free
+      if (lane == 0 && i + NS < n) issue_in(i + NS);
+      double g1[4];  // this row's flux along jgp
+#pragma unroll
+      for (int m = 0; m < 4; ++m) g1[m] = w2[m] * q[0].x[m];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double dvdy = A.dvv[0 * 4 + j] * g1[0];
+#pragma unroll
+        for (int m = 1; m < 4; ++m) dvdy = fma(A.dvv[m * 4 + j], g1[m], dvdy);
+        double acc = fma(rm[j], dvdy, q[0].x[j]);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc = fma(Ac[x][j], q[x].x[j], acc);
+        out.x[j] = acc;
+      }
+    } else {
+      Row g0, g1;  // the vector the weak divergence is taken of
+      if (OP == OP_DIVWK) {
+        ld_tile2(reinterpret_cast<const double*>(tile), sw2, g0, g1);
+      } else {
+        const Row sc = ld_tile(reinterpret_cast<const double*>(tile), sw1);
+        const Row a = deriv_i(sc, cx), b = deriv_j(sc, A.dvv);  // gradient_sphere (PO/sphere_operators.cpp:21-47)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          g0.x[j] = A.rrearth * fma(di[j][0], a.x[j], di[j][2] * b.x[j]);
+          g1.x[j] = A.rrearth * fma(di[j][1], a.x[j], di[j][3] * b.x[j]);
+        }
+        if (OP == OP_LAP_TENSOR) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double x0 = g0.x[j], x1 = g1.x[j];
+            g0.x[j] = fma(tv[j][0], x0, tv[j][1] * x1);
+            g1.x[j] = fma(tv[j][2], x0, tv[j][3] * x1);
+          }
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NO - 1) : "memory");
+      __syncwarp();
+      if (lane == 0 && i + NS < n) issue_in(i + NS);
+      // divergence_sphere_wk: s = spheremp*rrearth * (Dinv . g);  div(r,n) = -(sum_j Dvv[r][j] s0(j,n) + sum_j Dvv[n][j] s1(r,j))
+      Row s0, s1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s0.x[j] = mp4[j] * fma(di[j][0], g0.x[j], di[j][1] * g1.x[j]);
+        s1.x[j] = mp4[j] * fma(di[j][2], g0.x[j], di[j][3] * g1.x[j]);
+      }
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        double acc = cr[0] * s0.x[nn];
+#pragma unroll
+        for (int x = 1; x < 4; ++x) acc = fma(cr[x], __shfl_xor_sync(FULL, s0.x[nn], x), acc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fma(A.dvv[nn * 4 + j], s1.x[j], acc);
+        out.x[nn] = -acc;
+      }
+    }
+    unsigned char* otile = out_tiles + (i % NO) * OUT_B;
+    st_tile(reinterpret_cast<double*>(otile), sw1, out);
+    fence_proxy_async();
+    __syncwarp();  // the output tile is complete and visible to the TMA engine
+    if (lane == 0) {
+      tma_store(&M.out, lev0, OP == OP_EULER ? e * A.qsize_d + iq : e, otile);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk stores
+}
+
+// ---- CAAR_MODE_STRICT: the reference's operation order, one thread per point, 16 levels per CTA ------------------
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+
+struct StrictWkArgs {
+  const double* Dinv;
+  const double* spheremp;
+  const double* tensorvisc;
+  const double* vin;   // [E][L][16][2]
+  const double* sin;   // [E][L][16]
+  double* out;         // [E][L][16]
+  int nlev, nets, nelem_run, op;
+  double rrearth;
+  double dvv[16];
+};
+
+__global__ void __launch_bounds__(256) sphere_wk_strict_kernel(const StrictWkArgs A) {
+  __shared__ double g[16][16][2];  // per level of this CTA: the vector field the weak divergence is taken of
+  __shared__ double sc[16][16];
+  const int t = threadIdx.x, kl = t >> 4, q = t & 15, i = q >> 2, j = q & 3;
+  const long long rows = (long long)A.nelem_run * A.nlev;
+  const long long gk0 = (long long)blockIdx.x * 16 + kl;
+  const bool live = gk0 < rows;
+  const long long gk = live ? gk0 : rows - 1;
+  const size_t e = (size_t)A.nets + (size_t)(gk / A.nlev);
+  const size_t n = (e * A.nlev + (size_t)(gk % A.nlev)) * 16;
+  const double* dinv = A.Dinv + e * 64;
+  if (A.op == 0) {
+    g[kl][q][0] = A.vin[(n + q) * 2];
+    g[kl][q][1] = A.vin[(n + q) * 2 + 1];
+  } else {
+    sc[kl][q] = A.sin[n + q];
+  }
+  __syncthreads();
+  if (A.op != 0) {  // gradient_sphere at point (i,j) in the reference's order (PO/sphere_operators.cpp:21-47)
+    double sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      sx = add(sx, mul(A.dvv[m * 4 + i], sc[kl][m * 4 + j]));
+      sy = add(sy, mul(A.dvv[m * 4 + j], sc[kl][i * 4 + m]));
+    }
+    const double a = mul(sx, A.rrearth), b = mul(sy, A.rrearth);
+    const double* di = dinv + q * 4;
+    double g0 = add(mul(di[0], a), mul(di[2], b));
+    double g1 = add(mul(di[1], a), mul(di[3], b));
+    if (A.op == 2) {  // tensorVisc . grad (LV/SphereOperators.hpp:574-585)
+      const double* tv = A.tensorvisc + e * 64 + q * 4;
+      const double x0 = g0, x1 = g1;
+      g0 = add(mul(tv[0], x0), mul(tv[1], x1));
+      g1 = add(mul(tv[2], x0), mul(tv[3], x1));
+    }
+    g[kl][q][0] = g0;
+    g[kl][q][1] = g1;
+  }
+  __syncthreads();
+  // divergence_sphere_wk at point (m,n) = (i,j) (LV/SphereOperators.hpp:493-535)
+  const double* mp = A.spheremp + e * 16;
+  double dd = 0.0;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int pa = jj * 4 + j, pb = i * 4 + jj;  // points (jj, n) and (m, jj)
+    const double ta = add(mul(dinv[pa * 4 + 0], g[kl][pa][0]), mul(dinv[pa * 4 + 1], g[kl][pa][1]));
+    const double tb = add(mul(dinv[pb * 4 + 2], g[kl][pb][0]), mul(dinv[pb * 4 + 3], g[kl][pb][1]));
+    const double term = mul(add(mul(mul(mp[pa], ta), A.dvv[i * 4 + jj]), mul(mul(mp[pb], tb), A.dvv[j * 4 + jj])), A.rrearth);
+    dd = __dsub_rn(dd, term);
+  }
+  if (live) A.out[n + q] = dd;
+}
+
+int encode3(CUtensorMap* m, const void* base, cuuint64_t slices, cuuint64_t rows, cuuint32_t box_rows) {
+  typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_t encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return 1;
+    encode = reinterpret_cast<encode_t>(fn);
+  }
+  const cuuint64_t gdim[3] = {16, rows, slices};
+  const cuuint64_t gstride[2] = {128, rows * 128};
+  const cuuint32_t box[3] = {16, box_rows, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
+template <int OP>
+cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s) {
+  const unsigned in_b = (OP == OP_DIVWK) ? 2048u : 1024u, item_b = (OP == OP_EULER) ? 2048u : 0u;
+  const size_t smem = (size_t)WPC * (NS * in_b + NO * 1024u + 2 * item_b) + WPC * (NS + 2) * sizeof(uint64_t) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levelop_kernel<OP>, 32 * WPC, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  static const int waves = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 1; }();
+  long long blocks = (long long)sm_count() * per_sm * (waves > 0 ? waves : 1);  // persistent: every warp a pipeline
+  const long long need = (a.units + WPC - 1) / WPC;
+  if (blocks > need) blocks = need;
+  levelop_kernel<OP><<<(unsigned)blocks, 32 * WPC, smem, s>>>(a, m);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// Level-local operator on elements [nets,nete). op: 0 tracer step (in = Qdp mirror, item = vstar, out = qtens),
+// 1 divergence_sphere_wk (in = vector [E][L][16][2]), 2 laplace_simple, 3 laplace_tensor (in = scalar [E][L][16]);
+// out [E][L][16] (tracer step: [E][qsize_d][L][16]). in == out is allowed for 2 and 3 (the reference's *_replace).
+cudaError_t launch_levelop(int op, const KernelArgs& k, const double* in, const double* item, double* out,
+                           const double* tensorvisc, int nets, int nete, int qn0, int qsize, double dt, bool strict,
+                           cudaStream_t s) {
+  if (nete <= nets || (op == 0 && qsize <= 0)) return cudaSuccess;
+  if (strict) {
+    if (op == 0) return cudaErrorInvalidValue;  // the strict tracer step lives in caar_euler.cu
+    StrictWkArgs a;
+    a.Dinv = k.Dinv; a.spheremp = k.spheremp; a.tensorvisc = tensorvisc; a.vin = in; a.sin = in; a.out = out;
+    a.nlev = k.nlev; a.nets = nets; a.nelem_run = nete - nets; a.op = op - 1; a.rrearth = k.rrearth;
+    for (int i = 0; i < 16; ++i) a.dvv[i] = k.dvv[i];
+    const long long rows = (long long)(nete - nets) * k.nlev;
+    sphere_wk_strict_kernel<<<(unsigned)((rows + 15) / 16), 256, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  LevelOpArgs a;
+  a.Dinv = k.Dinv; a.metdet = k.metdet; a.rmetdet = k.rmetdet; a.spheremp = k.spheremp; a.tensorvisc = tensorvisc;
+  a.nlev = k.nlev; a.nets = nets; a.qn0 = qn0; a.qsize_d = k.qsize_d; a.dt = dt; a.rrearth = k.rrearth;
+  for (int i = 0; i < 16; ++i) a.dvv[i] = k.dvv[i];
+  a.ngroups = (k.nlev + GL - 1) / GL;  // groups of 8 levels; the last one may stick out of the column (zero-filled / clipped)
+  a.Q = op == 0 ? qsize : 1;
+  a.units = (long long)(nete - nets) * a.ngroups * a.Q;
+  LevelOpMaps m;
+  const cuuint64_t E = (cuuint64_t)k.nelem, L = (cuuint64_t)k.nlev;
+  int bad = 0;
+  if (op == 0) {
+    bad |= encode3(&m.in, in, E * (cuuint64_t)k.qsize_d * 2, L, GL);
+    bad |= encode3(&m.item, item, E, 2 * L, 2 * GL);
+    bad |= encode3(&m.out, out, E * (cuuint64_t)k.qsize_d, L, GL);
+  } else {
+    bad |= encode3(&m.in, in, E, op == 1 ? 2 * L : L, op == 1 ? 2 * GL : GL);
+    bad |= encode3(&m.out, out, E, L, GL);
+    m.item = m.in;
+  }
+  if (bad) return cudaErrorInvalidValue;
+  switch (op) {
+    case 0: return launch_op<OP_EULER>(a, m, s);
+    case 1: return launch_op<OP_DIVWK>(a, m, s);
+    case 2: return launch_op<OP_LAP_SIMPLE>(a, m, s);
+    case 3: return launch_op<OP_LAP_TENSOR>(a, m, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace caar

@@ -7,7 +7,7 @@ here=$(cd "$(dirname "$0")" && pwd)
 src=$here/../tinman_sandbox_b200/csrc
 out=$here/_variants
 mkdir -p $out/obj_$name
-for f in caar_capi caar_fused caar_fused_more caar_strict caar_aux caar_euler; do
+for f in caar_capi caar_fused caar_fused_more caar_strict caar_aux caar_euler caar_levelops; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC \
     -I$here/../include -I$src $flags -Xptxas -v -c $src/$f.cu -o $out/obj_$name/$f.o 2> $out/obj_$name/$f.ptxas.log &
 done
