@@ -52,6 +52,30 @@ def test_standalone_driver_prints_reference_norms(mode, golden_dir):
     assert np.max(np.abs(_vals(out2) - want) / want) < 1e-13
 
 
+def test_standalone_driver_checksums_do_not_depend_on_the_partition():
+    """--caar-checksums: per-GPU caar_checksums summed over ranks (NCCL when more than one GPU is visible). In strict
+    mode the exact bit-pattern sums printed for 1 GPU equal the CPU reference's (bit-identical data), and a multi-GPU
+    run — any partition — prints the same ones."""
+    import torch
+    from oracle import harness
+    exe = os.path.join(HOST, "caar_driver")
+    orc = harness.best_oracle(72)
+    s = orc.init(10)
+    orc.run(s)
+    want = {}
+    for name, short in (("elem_state_dp3d", "dp3d"), ("elem_state_v", "v"), ("elem_state_T", "T"),
+                        ("elem_derived_eta_dot_dpdn", "eta_dot_dpdn"), ("elem_derived_omega_p", "omega_p"),
+                        ("elem_derived_phi", "phi"), ("elem_derived_vn0", "vn0")):
+        a = s.arrays[name][:, 1] if name.startswith("elem_state") and name != "elem_state_phis" else s.arrays[name]
+        want[short] = format(int(np.ascontiguousarray(a).view(np.uint64).sum(dtype=np.uint64)), "016x")
+    gpus = [1] + ([2] if torch.cuda.device_count() >= 2 else [])
+    for g in gpus:
+        out = subprocess.run([exe, "--caar-mode=strict", "--caar-checksums=yes", f"--caar-gpus={g}"], capture_output=True,
+                             text=True, check=True).stdout
+        got = {m.group(1): m.group(2) for m in re.finditer(r"^\s+(\w+)\s+\S+\s+\S+\s+([0-9a-f]{16})$", out, re.M)}
+        assert got == want, (g, got, want)
+
+
 def test_driver_cli_errors():
     exe = os.path.join(HOST, "caar_driver")
     assert subprocess.run([exe, "--tinman-num-elems=abc"], capture_output=True).returncode == 1

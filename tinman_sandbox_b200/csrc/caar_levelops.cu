@@ -41,9 +41,21 @@
 namespace caar {
 namespace {
 
-constexpr int NS = 4;   // input tiles in flight per warp
-constexpr int NO = 2;   // output tiles in flight per warp
-constexpr int WPC = 4;  // warps per CTA (independent pipelines: no CTA-wide barrier after the prologue)
+#ifndef LEVELOP_NS
+#define LEVELOP_NS 4
+#endif
+#ifndef LEVELOP_NO
+#define LEVELOP_NO 2
+#endif
+#ifndef LEVELOP_WPC
+#define LEVELOP_WPC 4
+#endif
+#ifndef LEVELOP_MINB
+#define LEVELOP_MINB 4
+#endif
+constexpr int NS = LEVELOP_NS;    // input tiles in flight per warp
+constexpr int NO = LEVELOP_NO;    // output tiles in flight per warp
+constexpr int WPC = LEVELOP_WPC;  // warps per CTA (independent pipelines: no CTA-wide barrier after the prologue)
 constexpr int GL = 8;   // levels per tile = levels per warp (8 levels x 4 GLL rows = 32 lanes)
 
 struct LevelOpArgs {
@@ -89,7 +101,7 @@ enum { OP_EULER = 0, OP_DIVWK = 1, OP_LAP_SIMPLE = 2, OP_LAP_TENSOR = 3 };
 // fastest: its lane 0 issues the TMA loads NS tiles ahead and the TMA stores, the warp waits on its own mbarriers and
 // synchronises with __syncwarp only.
 template <int OP>
-__global__ void __launch_bounds__(32 * WPC, 4) levelop_kernel(const __grid_constant__ LevelOpArgs A,
+__global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const __grid_constant__ LevelOpArgs A,
                                                               const __grid_constant__ LevelOpMaps M) {
   constexpr unsigned IN_B = (OP == OP_DIVWK) ? 2048u : 1024u;  // bytes of a streamed input tile (8 levels)
   constexpr unsigned OUT_B = 1024u, ITEM_B = (OP == OP_EULER) ? 2048u : 0u;
@@ -103,41 +115,62 @@ __global__ void __launch_bounds__(32 * WPC, 4) levelop_kernel(const __grid_const
   uint64_t* full = reinterpret_cast<uint64_t*>(base + WPC * WARP_B) + w * (NS + 2);  // [NS] input stages, [2] item tiles
   uint64_t* item_full = full + NS;
 
-  const int Q = A.Q;
+  const int Q = A.Q, NG = A.ngroups;
   const long long wid = (long long)blockIdx.x * WPC + w, nwarps = (long long)gridDim.x * WPC;
   const long long u0 = A.units * wid / nwarps, u1 = A.units * (wid + 1) / nwarps;
   const int n = (int)(u1 - u0);
   if (n <= 0) return;  // whole warp
+  // OP_EULER: this warp's cache of the element's geometry, [row][met*Dinv (16) | -dt*rmetdet*rrearth (4)]
+  double* geo = reinterpret_cast<double*>(base + WPC * WARP_B + WPC * (NS + 2) * sizeof(uint64_t)) + w * 80;
 
   // swizzled offsets of this lane's data inside a scalar tile (row = level) and a (u,v) tile (row = 2*level + r/2)
   const uint32_t sw1 = (uint32_t)lvl * 128u + ((uint32_t)((2 * r) ^ (lvl & 7)) << 4);
   const uint32_t sw2 = (uint32_t)(lane >> 1) * 128u + ((uint32_t)((4 * (r & 1)) ^ ((lane >> 1) & 7)) << 4);
 
-  auto issue_in = [&](int i) {  // unit i of this warp -> stage i % NS (lane 0 only)
-    const long long u = u0 + i;
-    const long long item = u / Q;
-    const int iq = (int)(u - item * Q);
-    const int e = A.nets + (int)(item / A.ngroups), lev0 = (int)(item % A.ngroups) * GL;
-    const int s = i % NS;
-    mbar_expect_tx(&full[s], IN_B);
-    if (OP == OP_EULER) tma_load(in_tiles + s * IN_B, &M.in, lev0, (e * A.qsize_d + iq) * 2 + A.qn0, &full[s]);
-    else if (OP == OP_DIVWK) tma_load(in_tiles + s * IN_B, &M.in, lev0 * 2, e, &full[s]);
-    else tma_load(in_tiles + s * IN_B, &M.in, lev0, e, &full[s]);
+  // (element, group, tracer) of a unit, advanced without divisions: tracer fastest, then group, then element
+  struct Pos {
+    int e, g, iq;
   };
-  auto issue_item = [&](long long item, int k) {  // vstar of (element, group) -> item buffer k % 2 (lane 0 only)
-    const int e = A.nets + (int)(item / A.ngroups), lev0 = (int)(item % A.ngroups) * GL;
+  auto advance = [&](Pos& p) {
+    if (++p.iq == Q) {
+      p.iq = 0;
+      if (++p.g == NG) p.g = 0, ++p.e;
+    }
+  };
+  Pos cur, pre, pitem;  // the unit being computed, the next unit to prefetch, the next (element, group) whose vstar to fetch
+  {
+    const long long item0 = u0 / Q;
+    cur.iq = (int)(u0 - item0 * Q);
+    cur.e = A.nets + (int)(item0 / NG);
+    cur.g = (int)(item0 % NG);
+    pre = cur;
+    pitem = cur;
+    pitem.iq = 0;
+  }
+  int items_left = (int)((u0 + n - 1) / Q - u0 / Q) + 1;  // vstar tiles this warp will need
+
+  auto issue_in = [&](int i) {  // unit `pre` -> stage i % NS (lane 0 only); advances `pre`
+    const int s = i % NS, lev0 = pre.g * GL;
+    mbar_expect_tx(&full[s], IN_B);
+    if (OP == OP_EULER) tma_load(in_tiles + s * IN_B, &M.in, lev0, (pre.e * A.qsize_d + pre.iq) * 2 + A.qn0, &full[s]);
+    else if (OP == OP_DIVWK) tma_load(in_tiles + s * IN_B, &M.in, lev0 * 2, pre.e, &full[s]);
+    else tma_load(in_tiles + s * IN_B, &M.in, lev0, pre.e, &full[s]);
+    advance(pre);
+  };
+  auto issue_item = [&](int k) {  // vstar of `pitem` -> item buffer k % 2 (lane 0 only); advances `pitem`
     mbar_expect_tx(&item_full[k & 1], ITEM_B);
-    tma_load(item_tiles + (k & 1) * ITEM_B, &M.item, lev0 * 2, e, &item_full[k & 1]);
+    tma_load(item_tiles + (k & 1) * ITEM_B, &M.item, pitem.g * GL * 2, pitem.e, &item_full[k & 1]);
+    if (++pitem.g == NG) pitem.g = 0, ++pitem.e;
+    --items_left;
   };
 
-  const long long item0 = u0 / Q, item_last = (u0 + n - 1) / Q;
   if (lane == 0) {
     for (int s = 0; s < NS + 2; ++s) mbar_init(&full[s], 1);
     fence_proxy_async();
     for (int i = 0; i < NS && i < n; ++i) issue_in(i);
     if (OP == OP_EULER) {
-      issue_item(item0, 0);
-      if (item_last > item0) issue_item(item0 + 1, 1);
+      issue_item(0);
+      if (items_left > 0) issue_item(1);
     }
   }
   __syncwarp();
@@ -158,46 +191,56 @@ __global__ void __launch_bounds__(32 * WPC, 4) levelop_kernel(const __grid_const
     }
   }
 
-  long long cur_item = -1;
-  int cur_e = -1, item_k = -1;
-  // per-element state: this row's geometry
-  double di[4][4], met[4], rm[4], mp4[4], tv[4][4];
-  // per-item state (OP_EULER): Ac[x][j] = rm[j] Dvv[r^x][r] w1(r^x, j) for row r^x, and this row's w2
-  double Ac[4][4], w2[4];
-  int e = 0, lev0 = 0;
+  bool new_item = true, new_elem = true;
+  int item_k = -1;
+  // weak-form operators: this row's geometry in registers (once per element)
+  double di[4][4], mp4[4], tv[4][4];
+  // OP_EULER: per-item coefficients Ac[x][j] = rm[j] Dvv[r^x][r] w1(r^x, j) for row r^x, this row's w2, and rm
+  double Ac[4][4], w2[4], rm[4];
 
   for (int i = 0; i < n; ++i) {
-    const long long u = u0 + i;
-    const long long item = u / Q;
-    const int iq = (int)(u - item * Q);
-    if (item != cur_item) {  // uniform over the warp
-      cur_item = item;
+    const int e = cur.e, lev0 = cur.g * GL, iq = cur.iq;
+    if (new_item) {  // uniform over the warp
       ++item_k;
-      e = A.nets + (int)(item / A.ngroups);
-      lev0 = (int)(item % A.ngroups) * GL;
-      if (e != cur_e) {  // this row's geometry: once per element, reused over its level groups and tracers
-        cur_e = e;
+      if (new_elem) {  // once per element, reused over its level groups and tracers
         const size_t ge = (size_t)e;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double2 a = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4));
-          const double2 b = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4 + 2));
-          di[j][0] = a.x; di[j][1] = a.y; di[j][2] = b.x; di[j][3] = b.y;
-          if (OP == OP_LAP_TENSOR) {
-            const double2 c = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4));
-            const double2 d = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4 + 2));
-            tv[j][0] = c.x; tv[j][1] = c.y; tv[j][2] = d.x; tv[j][3] = d.y;
-          }
-        }
         if (OP == OP_EULER) {
-          const double2 a = __ldg(reinterpret_cast<const double2*>(A.metdet + ge * 16 + r * 4));
-          const double2 b = __ldg(reinterpret_cast<const double2*>(A.metdet + ge * 16 + r * 4 + 2));
-          met[0] = a.x; met[1] = a.y; met[2] = b.x; met[3] = b.y;
-          const double2 c = __ldg(reinterpret_cast<const double2*>(A.rmetdet + ge * 16 + r * 4));
-          const double2 d = __ldg(reinterpret_cast<const double2*>(A.rmetdet + ge * 16 + r * 4 + 2));
-          const double sc = -A.dt * A.rrearth;  // rm = -dt * rmetdet * rrearth
-          rm[0] = c.x * sc; rm[1] = c.y * sc; rm[2] = d.x * sc; rm[3] = d.y * sc;
+          __syncwarp();  // the previous element's cache is no longer being read
+          if (lvl == 0) {  // the four lanes r = 0..3 fill the warp's geometry cache
+            double m4[4], r4[4];
+            const double2 a = __ldg(reinterpret_cast<const double2*>(A.metdet + ge * 16 + r * 4));
+            const double2 b = __ldg(reinterpret_cast<const double2*>(A.metdet + ge * 16 + r * 4 + 2));
+            m4[0] = a.x; m4[1] = a.y; m4[2] = b.x; m4[3] = b.y;
+            const double2 c = __ldg(reinterpret_cast<const double2*>(A.rmetdet + ge * 16 + r * 4));
+            const double2 d = __ldg(reinterpret_cast<const double2*>(A.rmetdet + ge * 16 + r * 4 + 2));
+            const double sc = -A.dt * A.rrearth;
+            r4[0] = c.x * sc; r4[1] = c.y * sc; r4[2] = d.x * sc; r4[3] = d.y * sc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double2 p0 = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4));
+              const double2 p1 = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4 + 2));
+              *reinterpret_cast<double2*>(geo + r * 20 + j * 4) = make_double2(m4[j] * p0.x, m4[j] * p0.y);
+              *reinterpret_cast<double2*>(geo + r * 20 + j * 4 + 2) = make_double2(m4[j] * p1.x, m4[j] * p1.y);
+            }
+            *reinterpret_cast<double2*>(geo + r * 20 + 16) = make_double2(r4[0], r4[1]);
+            *reinterpret_cast<double2*>(geo + r * 20 + 18) = make_double2(r4[2], r4[3]);
+          }
+          __syncwarp();
+          const double2 a = *reinterpret_cast<const double2*>(geo + r * 20 + 16);
+          const double2 b = *reinterpret_cast<const double2*>(geo + r * 20 + 18);
+          rm[0] = a.x; rm[1] = a.y; rm[2] = b.x; rm[3] = b.y;
         } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4));
+            const double2 b = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4 + 2));
+            di[j][0] = a.x; di[j][1] = a.y; di[j][2] = b.x; di[j][3] = b.y;
+            if (OP == OP_LAP_TENSOR) {
+              const double2 c = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4));
+              const double2 d = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4 + 2));
+              tv[j][0] = c.x; tv[j][1] = c.y; tv[j][2] = d.x; tv[j][3] = d.y;
+            }
+          }
           const double2 a = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4));
           const double2 b = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4 + 2));
           mp4[0] = a.x * A.rrearth; mp4[1] = a.y * A.rrearth; mp4[2] = b.x * A.rrearth; mp4[3] = b.y * A.rrearth;
@@ -208,12 +251,14 @@ __global__ void __launch_bounds__(32 * WPC, 4) levelop_kernel(const __grid_const
         Row us, vs;
         ld_tile2(reinterpret_cast<const double*>(item_tiles + (item_k & 1) * ITEM_B), sw2, us, vs);
         __syncwarp();  // every lane has read the vstar tile: its buffer may be refilled (two items ahead)
-        if (lane == 0 && item + 2 <= item_last) issue_item(item + 2, item_k + 2);
+        if (lane == 0 && items_left > 0) issue_item(item_k + 2);
         double w1[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          w1[j] = met[j] * fma(di[j][0], us.x[j], di[j][1] * vs.x[j]);
-          w2[j] = met[j] * fma(di[j][2], us.x[j], di[j][3] * vs.x[j]);
+        for (int j = 0; j < 4; ++j) {  // (w1, w2) = metdet Dinv vstar
+          const double2 p0 = *reinterpret_cast<const double2*>(geo + r * 20 + j * 4);
+          const double2 p1 = *reinterpret_cast<const double2*>(geo + r * 20 + j * 4 + 2);
+          w1[j] = fma(p0.x, us.x[j], p0.y * vs.x[j]);
+          w2[j] = fma(p1.x, us.x[j], p1.y * vs.x[j]);
         }
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -224,6 +269,10 @@ __global__ void __launch_bounds__(32 * WPC, 4) levelop_kernel(const __grid_const
           }
       }
     }
+    // position of the next unit, and whether it starts a new item / element
+    advance(cur);
+    new_item = cur.iq == 0;
+    new_elem = new_item && cur.g == 0;
 
     const int s = i % NS;
     mbar_wait(&full[s], (i / NS) & 1);
@@ -398,7 +447,8 @@ int encode3(CUtensorMap* m, const void* base, cuuint64_t slices, cuuint64_t rows
 template <int OP>
 cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s) {
   const unsigned in_b = (OP == OP_DIVWK) ? 2048u : 1024u, item_b = (OP == OP_EULER) ? 2048u : 0u;
-  const size_t smem = (size_t)WPC * (NS * in_b + NO * 1024u + 2 * item_b) + WPC * (NS + 2) * sizeof(uint64_t) + 1024;
+  const size_t smem = (size_t)WPC * (NS * in_b + NO * 1024u + 2 * item_b) + WPC * (NS + 2) * sizeof(uint64_t) +
+                      WPC * 80 * sizeof(double) + 1024;
   cudaError_t e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);

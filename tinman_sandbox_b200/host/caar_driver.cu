@@ -4,7 +4,7 @@
 // (compute_and_apply_rhs.cpp:372-399) so the two outputs can be diffed — but the state lives on the GPUs.
 //
 //   caar_driver --tinman-num-elems=N --tinman-num-exec=M [--tinman-dump-res=yes|no]
-//               [--caar-nlev=72] [--caar-mode=fast|strict] [--caar-gpus=G] [--caar-resident=yes|no]
+//               [--caar-nlev=72] [--caar-mode=fast|strict] [--caar-gpus=G] [--caar-resident=yes|no] [--caar-checksums=yes|no]
 //
 // Multi-GPU: the element range is cut into G contiguous blocks [g*N/G, (g+1)*N/G) — the reference's own
 // nets/nete partition hook (data_structures.hpp:58-66) — one host thread and one C-ABI handle per GPU, no
@@ -33,7 +33,7 @@ using caar_host::init_data;
 
 struct Options {
   int num_elems = 10, num_exec = 1, nlev = 72, gpus = 1, mode = CAAR_MODE_FAST;
-  bool dump = false, resident = true;
+  bool dump = false, resident = true, checksums = false;
 };
 
 [[noreturn]] void die(const char* what, int rc) {
@@ -87,6 +87,63 @@ void reduce_norms(std::vector<Rank>& ranks, std::vector<ncclComm_t>& comms, int 
     cudaFree(buf[g]);
     cudaStreamDestroy(st[g]);
   }
+}
+
+// The other collective of the job (north star: "final allreduce of field checksums and energy norms"): per-GPU
+// caar_checksums summed over ranks — sums, sums of squares and the two energy norms as doubles, the exact bit-pattern
+// sums as 64-bit integers (wrap-around addition is associative, so the result does not depend on the partition).
+void reduce_checksums(std::vector<Rank>& ranks, std::vector<ncclComm_t>& comms, int tl, caar_checksum* out) {
+  const int G = (int)ranks.size();
+  std::vector<caar_checksum> cs(G);
+  for (int g = 0; g < G; ++g) OK(caar_checksums(ranks[g].h, tl, 0, ranks[g].n, &cs[g]));
+  *out = cs[0];
+  if (G == 1) return;
+  std::vector<double*> fbuf(G);
+  std::vector<unsigned long long*> ibuf(G);
+  std::vector<cudaStream_t> st(G);
+  for (int g = 0; g < G; ++g) {
+    double f[16];
+    std::memcpy(f, cs[g].sum, 7 * sizeof(double));
+    std::memcpy(f + 7, cs[g].sumsq, 7 * sizeof(double));
+    std::memcpy(f + 14, cs[g].energy, 2 * sizeof(double));
+    cudaSetDevice(ranks[g].device);
+    cudaMalloc(&fbuf[g], sizeof f);
+    cudaMalloc(&ibuf[g], sizeof cs[g].bits);
+    cudaStreamCreate(&st[g]);
+    cudaMemcpy(fbuf[g], f, sizeof f, cudaMemcpyHostToDevice);
+    cudaMemcpy(ibuf[g], cs[g].bits, sizeof cs[g].bits, cudaMemcpyHostToDevice);
+  }
+  ncclGroupStart();
+  for (int g = 0; g < G; ++g) {
+    ncclAllReduce(fbuf[g], fbuf[g], 16, ncclDouble, ncclSum, comms[g], st[g]);
+    ncclAllReduce(ibuf[g], ibuf[g], 7, ncclUint64, ncclSum, comms[g], st[g]);
+  }
+  ncclGroupEnd();
+  for (int g = 0; g < G; ++g) {
+    cudaSetDevice(ranks[g].device);
+    cudaStreamSynchronize(st[g]);
+  }
+  double f[16];
+  cudaSetDevice(ranks[0].device);
+  cudaMemcpy(f, fbuf[0], sizeof f, cudaMemcpyDeviceToHost);
+  cudaMemcpy(out->bits, ibuf[0], sizeof out->bits, cudaMemcpyDeviceToHost);
+  std::memcpy(out->sum, f, 7 * sizeof(double));
+  std::memcpy(out->sumsq, f + 7, 7 * sizeof(double));
+  std::memcpy(out->energy, f + 14, 2 * sizeof(double));
+  for (int g = 0; g < G; ++g) {
+    cudaSetDevice(ranks[g].device);
+    cudaFree(fbuf[g]);
+    cudaFree(ibuf[g]);
+    cudaStreamDestroy(st[g]);
+  }
+}
+
+void print_checksums(const caar_checksum& c) {
+  static const char* const name[7] = {"dp3d", "v", "T", "eta_dot_dpdn", "omega_p", "phi", "vn0"};
+  std::printf("   ---> Checksums (sum, sum of squares, bit-pattern sum mod 2^64):\n");
+  for (int f = 0; f < 7; ++f)
+    std::printf("          %-13s %.17g %.17g %016llx\n", name[f], c.sum[f], c.sumsq[f], c.bits[f]);
+  std::printf("          energy: kinetic %.17g internal %.17g\n", c.energy[0], c.energy[1]);
 }
 
 void dump(const HostData& d) {
@@ -149,6 +206,7 @@ int main(int argc, char** argv) {
     } else if (key == "--tinman-num-exec") o.num_exec = std::atoi(val.c_str());
     else if (key == "--tinman-dump-res") yesno(o.dump);
     else if (key == "--caar-resident") yesno(o.resident);
+    else if (key == "--caar-checksums") yesno(o.checksums);
     else if (key == "--caar-nlev") o.nlev = std::atoi(val.c_str());
     else if (key == "--caar-gpus") o.gpus = std::atoi(val.c_str());
     else if (key == "--caar-mode") o.mode = (val == "strict") ? CAAR_MODE_STRICT : CAAR_MODE_FAST;
@@ -157,7 +215,7 @@ int main(int argc, char** argv) {
                   "  --tinman-dump-res=val : whether to dump results to file (default=no)\n"
                   "  --tinman-num-exec=N   : number of times to execute (default=1)\n"
                   "  --caar-nlev=L         : vertical levels (default=72)\n"
-                  "  --caar-mode=fast|strict, --caar-gpus=G, --caar-resident=yes|no\n"
+                  "  --caar-mode=fast|strict, --caar-gpus=G, --caar-resident=yes|no, --caar-checksums=yes|no\n"
                   "  --tinman-help         : prints this message\n");
       return 0;
     }
@@ -235,6 +293,11 @@ int main(int argc, char** argv) {
               G > 1 ? "s" : "", (double)o.num_elems * o.nlev * o.num_exec / sec);
   reduce_norms(ranks, comms, d.ctl.np1, ss);
   print_norms(ss);
+  if (o.checksums) {
+    caar_checksum cs;
+    reduce_checksums(ranks, comms, d.ctl.np1, &cs);
+    print_checksums(cs);
+  }
 
   if (o.dump) {
     std::printf(" --- Dumping results to file...\n");
