@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const _
 
   bool new_item = true, new_elem = true;
   int item_k = -1;
-  // weak-form operators: this row's geometry in registers (once per element)
-  double di[4][4], mp4[4], tv[4][4];
+  // weak-form operators: this row's point-local 2x2 matrices in registers (once per element)
+  double nm[4][4];
   // OP_EULER: per-item coefficients Ac[x][j] = rm[j] Dvv[r^x][r] w1(r^x, j) for row r^x, this row's w2, and rm
   double Ac[4][4], w2[4], rm[4];
 
@@ -230,20 +230,34 @@ __global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const _
           const double2 b = *reinterpret_cast<const double2*>(geo + r * 20 + 18);
           rm[0] = a.x; rm[1] = a.y; rm[2] = b.x; rm[3] = b.y;
         } else {
+          const double2 ma = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4));
+          const double2 mb = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4 + 2));
+          const double mpr[4] = {ma.x * A.rrearth, ma.y * A.rrearth, mb.x * A.rrearth, mb.y * A.rrearth};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const double2 a = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4));
             const double2 b = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + (r * 4 + j) * 4 + 2));
-            di[j][0] = a.x; di[j][1] = a.y; di[j][2] = b.x; di[j][3] = b.y;
-            if (OP == OP_LAP_TENSOR) {
-              const double2 c = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4));
-              const double2 d = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4 + 2));
-              tv[j][0] = c.x; tv[j][1] = c.y; tv[j][2] = d.x; tv[j][3] = d.y;
+            if (OP == OP_DIVWK) {  // s = (spheremp rrearth Dinv) . v
+              nm[j][0] = mpr[j] * a.x; nm[j][1] = mpr[j] * a.y; nm[j][2] = mpr[j] * b.x; nm[j][3] = mpr[j] * b.y;
+            } else {
+              // the whole point-local part of the laplacian as ONE 2x2 matrix per point, applied to the raw derivatives
+              // (a, b) of the scalar: grad = rrearth Dinv^T (a,b); [tensor: grad <- tensorVisc grad;] s = spheremp rrearth
+              // Dinv grad  =>  s = N (a,b), N = spheremp rrearth^2 Dinv [tensorVisc] Dinv^T
+              double t00 = a.x, t01 = b.x, t10 = a.y, t11 = b.y;  // Dinv^T: grad0 = di0 a + di2 b, grad1 = di1 a + di3 b
+              if (OP == OP_LAP_TENSOR) {
+                const double2 c = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4));
+                const double2 d = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + (r * 4 + j) * 4 + 2));
+                const double u00 = fma(c.x, t00, c.y * t10), u01 = fma(c.x, t01, c.y * t11);
+                const double u10 = fma(d.x, t00, d.y * t10), u11 = fma(d.x, t01, d.y * t11);
+                t00 = u00; t01 = u01; t10 = u10; t11 = u11;
+              }
+              const double sc = mpr[j] * A.rrearth;
+              nm[j][0] = sc * fma(a.x, t00, a.y * t10);
+              nm[j][1] = sc * fma(a.x, t01, a.y * t11);
+              nm[j][2] = sc * fma(b.x, t00, b.y * t10);
+              nm[j][3] = sc * fma(b.x, t01, b.y * t11);
             }
           }
-          const double2 a = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4));
-          const double2 b = __ldg(reinterpret_cast<const double2*>(A.spheremp + ge * 16 + r * 4 + 2));
-          mp4[0] = a.x * A.rrearth; mp4[1] = a.y * A.rrearth; mp4[2] = b.x * A.rrearth; mp4[3] = b.y * A.rrearth;
         }
       }
       if (OP == OP_EULER) {
@@ -303,35 +317,23 @@ __global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const _
         out.x[j] = acc;
       }
     } else {
-      Row g0, g1;  // the vector the weak divergence is taken of
+      Row g0, g1;  // the vector the point-local matrix is applied to: v, or the raw derivatives of the scalar
       if (OP == OP_DIVWK) {
         ld_tile2(reinterpret_cast<const double*>(tile), sw2, g0, g1);
       } else {
         const Row sc = ld_tile(reinterpret_cast<const double*>(tile), sw1);
-        const Row a = deriv_i(sc, cx), b = deriv_j(sc, A.dvv);  // gradient_sphere (PO/sphere_operators.cpp:21-47)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          g0.x[j] = A.rrearth * fma(di[j][0], a.x[j], di[j][2] * b.x[j]);
-          g1.x[j] = A.rrearth * fma(di[j][1], a.x[j], di[j][3] * b.x[j]);
-        }
-        if (OP == OP_LAP_TENSOR) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double x0 = g0.x[j], x1 = g1.x[j];
-            g0.x[j] = fma(tv[j][0], x0, tv[j][1] * x1);
-            g1.x[j] = fma(tv[j][2], x0, tv[j][3] * x1);
-          }
-        }
+        g0 = deriv_i(sc, cx);     // sum_m Dvv[m][r] s(m,j)   (PO/sphere_operators.cpp:21-35)
+        g1 = deriv_j(sc, A.dvv);  // sum_m Dvv[m][j] s(r,m)
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NO - 1) : "memory");
       __syncwarp();
       if (lane == 0 && i + NS < n) issue_in(i + NS);
-      // divergence_sphere_wk: s = spheremp*rrearth * (Dinv . g);  div(r,n) = -(sum_j Dvv[r][j] s0(j,n) + sum_j Dvv[n][j] s1(r,j))
+      // divergence_sphere_wk of s = N . g:  div(r,n) = -(sum_j Dvv[r][j] s0(j,n) + sum_j Dvv[n][j] s1(r,j))
       Row s0, s1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        s0.x[j] = mp4[j] * fma(di[j][0], g0.x[j], di[j][1] * g1.x[j]);
-        s1.x[j] = mp4[j] * fma(di[j][2], g0.x[j], di[j][3] * g1.x[j]);
+        s0.x[j] = fma(nm[j][0], g0.x[j], nm[j][1] * g1.x[j]);
+        s1.x[j] = fma(nm[j][2], g0.x[j], nm[j][3] * g1.x[j]);
       }
 #pragma unroll
       for (int nn = 0; nn < 4; ++nn) {
@@ -457,8 +459,12 @@ cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levelop_kernel<OP>, 32 * WPC, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  static const int waves = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 1; }();
-  long long blocks = (long long)sm_count() * per_sm * (waves > 0 ? waves : 1);  // persistent: every warp a pipeline
+  // grid = waves x the resident CTAs: one wave (fully persistent) is best for the shuffle-heavy weak-form operators,
+  // several shorter ranges per warp slot balance the tracer step better (A/B: 0.90 / 0.93 / 0.95 / 0.96 of the measured
+  // peak at 1 / 2 / 4 / 8 waves, qsize 4; laplace_simple 0.56 / 0.55 / 0.53 / 0.48) — profiles/README.md
+  static const int waves_env = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 0; }();
+  const int waves = waves_env > 0 ? waves_env : (OP == OP_EULER ? (a.Q >= 4 ? 6 : 2 * a.Q - 1) : 1);  // qsize 1 -> 1 wave
+  long long blocks = (long long)sm_count() * per_sm * waves;
   const long long need = (a.units + WPC - 1) / WPC;
   if (blocks > need) blocks = need;
   levelop_kernel<OP><<<(unsigned)blocks, 32 * WPC, smem, s>>>(a, m);
