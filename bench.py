@@ -304,30 +304,37 @@ def max_rel_err(got, want, names):
     return worst
 
 
-def link_probe(dev, nbytes=1 << 28):
-    """What this GPU's host link does right now, in this process: host->device alone, device->host alone and both at
-    once (pinned 256 MiB buffers, two streams, best of 3) — the denominator of the end-to-end number."""
+def link_probe(dev, h2d_bytes, d2h_bytes, total=1 << 29):
+    """What this GPU's host link does right now, in this process (pinned buffers, two streams, best of 4): host->device
+    alone, device->host alone, both at once with equal sizes (duplex), and both at once IN THE PROPORTION OF ONE e2e
+    STEP (h2d_bytes : d2h_bytes) — the time of that last probe, scaled to the step's bytes, is the link-bound time of a
+    step and the denominator of the end-to-end number."""
     import torch
-    hin = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    hout = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    din = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    dout = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    n_in = int(total * h2d_bytes / float(h2d_bytes + d2h_bytes)) // 4096 * 4096
+    n_out = int(total * d2h_bytes / float(h2d_bytes + d2h_bytes)) // 4096 * 4096
+    nmax = max(n_in, n_out, total // 2)
+    hin = torch.empty(nmax, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(nmax, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(nmax, dtype=torch.uint8, device=dev)
+    dout = torch.empty(nmax, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     res = {}
-    for name, do_in, do_out in (("h2d", True, False), ("d2h", False, True), ("duplex", True, True)):
+    half = total // 2
+    for name, bi, bo in (("h2d", half, 0), ("d2h", 0, half), ("duplex", half, half), ("step_mix", n_in, n_out)):
         best = 1e30
         for _ in range(4):
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            if do_in:
+            if bi:
                 with torch.cuda.stream(s1):
-                    din.copy_(hin, non_blocking=True)
-            if do_out:
+                    din[:bi].copy_(hin[:bi], non_blocking=True)
+            if bo:
                 with torch.cuda.stream(s2):
-                    hout.copy_(dout, non_blocking=True)
+                    hout[:bo].copy_(dout[:bo], non_blocking=True)
             torch.cuda.synchronize(dev)
             best = min(best, time.perf_counter() - t0)
-        res[name] = nbytes / best / 1e9
+        res[name] = max(bi, bo) / best / 1e9 if name != "step_mix" else best
+    res["step_mix_h2d_bytes"] = n_in
     return res
 
 
@@ -352,6 +359,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-target-s", type=float, default=15.0)
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check after the timed loops")
+    ap.add_argument("--no-clock-topup", action="store_true",
+                    help="do not continue the kernel loop after a short timed region to collect 5 clock samples (keeps the "
+                         "number of calls, hence the accumulators and their checksums, deterministic)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -441,7 +451,7 @@ def main():
     calls_done = args.warmup + 2 + args.steps
     # A timed region shorter than ~5 NVML samples (small or strong-scaled slices): keep the SAME load running, outside
     # the timed region, until the sampler has at least 5 — and say so; never print a clocks record with fewer.
-    if sampler and sampler.count_since_mark() < 5:
+    if sampler and sampler.count_since_mark() < 5 and not args.no_clock_topup:
         t_end = time.perf_counter() + 0.25
         while sampler.count_since_mark() < 5 and time.perf_counter() < t_end:
             h.compute_and_apply_rhs(args.steps, mode)
@@ -506,7 +516,8 @@ def main():
         if parity is not None:
             e2e_wins = sample_windows(E, seed=2000 + rank)
             e2e_states = oracle_states(td, e2e_wins, L)
-        link = link_probe(dev)
+        barrier()                                    # every rank probes its link at the same time
+        link = link_probe(dev, h2d, d2h)
         h.compute_and_apply_rhs_host(td.arrays, mode, args.e2e_chunk)
         barrier()
         t0 = time.perf_counter()
@@ -526,20 +537,27 @@ def main():
                 worst = max(worst, max_rel_err({n: td.arrays[n][a:b] for n in harness.MUTATED}, st.arrays, harness.MUTATED))
             parity["e2e_max_rel_err"] = worst
             parity["e2e_calls"] = 1 + args.e2e_steps
+        # link-bound time of one step = time of the proportional probe scaled to the step's bytes
+        t_link = link["step_mix"] * (h2d / float(link["step_mix_h2d_bytes"]))
         lk = torch.tensor([link["h2d"], link["d2h"], link["duplex"]], dtype=torch.float64, device=dev)
+        tl_ = torch.tensor([t_link], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(lk, op=dist.ReduceOp.MIN)       # the slowest rank's link bounds the job
+            dist.all_reduce(tl_, op=dist.ReduceOp.MAX)
         lk = lk.cpu().numpy()
+        t_link = float(tl_.item())
         h2d_rate = h2d * args.e2e_steps / dt / 1e9
         e2e = {"value": E_total * L * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * dt / args.e2e_steps,
                "pcie_gbs": {"h2d": h2d_rate, "d2h": d2h * args.e2e_steps / dt / 1e9},
                "link": {"h2d_gbs": float(lk[0]), "d2h_gbs": float(lk[1]), "duplex_peak_gbs": float(lk[2]),
-                        "frac": h2d_rate / float(lk[2]), "bound": "host link (PCIe), host->device direction",
-                        "how": "256 MiB pinned copies in this process just before the timed e2e steps, one GPU per rank "
-                               "and all ranks at once: alone each way, then both ways at once (duplex, per direction); "
-                               "min over ranks; frac = achieved host->device GB/s of the e2e steps / duplex"},
+                        "step_ms_at_link_speed": 1e3 * t_link, "frac": t_link / (dt / args.e2e_steps),
+                        "bound": "host link (PCIe) and, with several GPUs, the host's memory system behind it",
+                        "how": "pinned copies in this process just before the timed e2e steps, one GPU per rank and all "
+                               "ranks at once: each direction alone, both with equal sizes (duplex, GB/s per direction, min "
+                               "over ranks), and both in the byte proportion of one e2e step; step_ms_at_link_speed = that "
+                               "last probe scaled to the step's bytes (max over ranks); frac = it / the measured step"},
                "how": "caar_run_host per step: host arrays in, host arrays out (%s), copy-in | kernel | "
                       "copy-out pipelined over element chunks; PCIe-bound" %
                       ("pinned" if pin_ok else "PAGEABLE: pinning would take >60% of host RAM")}
