@@ -452,10 +452,14 @@ def main():
     # A timed region shorter than ~5 NVML samples (small or strong-scaled slices): keep the SAME load running, outside
     # the timed region, until the sampler has at least 5 — and say so; never print a clocks record with fewer.
     if sampler and sampler.count_since_mark() < 5 and not args.no_clock_topup:
-        t_end = time.perf_counter() + 0.25
-        while sampler.count_since_mark() < 5 and time.perf_counter() < t_end:
-            h.compute_and_apply_rhs(args.steps, mode)
-            calls_done += args.steps
+        t_end = time.perf_counter() + 2.0
+        batch = max(args.steps, int(0.02 / max(ms / args.steps * 1e-3, 1e-6)))   # >= 20 ms of the same kernel per sync
+        extra_cap = 500                       # the accumulators are compared with the oracle after the same number of calls
+        while sampler.count_since_mark() < 5 and time.perf_counter() < t_end and extra_cap > 0:
+            batch = min(batch, extra_cap)
+            h.compute_and_apply_rhs(batch, mode)
+            calls_done += batch
+            extra_cap -= batch
         sampler.extended = True
     barrier()
     clocks = sampler.stop() if sampler else None

@@ -22,7 +22,11 @@ for r in rows[hi + 1:]:
     if op.startswith("@"):
         op = src.split()[1]
     op = op.rstrip(";")
-    f = lambda n: int(float(r[col[n]] or 0)) if n in col else 0
+    def f(n):
+        try:
+            return int(float(r[col[n]] or 0)) if n in col else 0
+        except ValueError:      # a second header row / a text cell ("-")
+            return 0
     a = agg[op]
     a[0] += f("Instructions Executed")
     a[1] += f("L1 Wavefronts Shared")
