@@ -33,12 +33,20 @@ def run_gpu(state, ncalls=1, mode=tb.MODE_FAST):
     return nrm
 
 
+POINTWISE = {}   # field -> worst pointwise relative error seen in this session (reported at the end, not gated)
+
+
 def check(got, want, exact):
     for n in harness.FIELD_NAMES:
         if n not in harness.MUTATED or exact:
             assert np.array_equal(got.arrays[n], want.arrays[n]), n
         else:
             assert rel_err(got.arrays[n], want.arrays[n]) <= TOL, (n, rel_err(got.arrays[n], want.arrays[n]))
+            b = want.arrays[n]
+            mask = np.abs(b) > 1e-30 * max(float(np.max(np.abs(b))), 1e-300)
+            if mask.any():   # a cancelling field (omega_p) shows a scan-carry regression here first
+                e = float(np.max(np.abs(got.arrays[n][mask] - b[mask]) / np.abs(b[mask])))
+                POINTWISE[n] = max(POINTWISE.get(n, 0.0), e)
 
 
 @pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
@@ -702,3 +710,12 @@ def test_biharmonic_is_two_laplacians():
     got = h.download_extra(tb.X_SCALAR_OUT, (E, L, 4, 4))
     h.close()
     assert rel_err(got, want) <= 2 * TOL
+
+
+def test_zz_report_pointwise_errors(capsys):
+    """Not a gate: prints the worst POINTWISE relative error per field over every fast-mode comparison of this session
+    (the gate is field-normalised); run last by name."""
+    with capsys.disabled():
+        for n, e in sorted(POINTWISE.items()):
+            print(f"\n[pointwise] {n}: max |a-b|/|b| = {e:.3e}", end="")
+        print()

@@ -28,7 +28,10 @@
 //   c(r,j) = -dt rmetdet(r,j) rrearth,  A(m,j) = c(r,j) Dvv[m][r] w1(m,j),  (w1,w2) = metdet Dinv vstar
 //   — no shuffles and no geometry loads inside the tracer loop.
 // The weak-form operators use the fused kernel's row decomposition: sums along jgp thread-local, sums along igp through
-// three xor-shuffles per value.
+// three xor-shuffles per value. Tried and rejected (profiles/README.md): exchanging the rows through the shared-memory
+// tile instead of shuffles (80 fewer instructions per tile, two more __syncwarp round trips: 0.66 vs 0.70 for
+// laplace_simple), and computing the per-element coefficients in a pre-pass kernel with a bulk-copy prefetch two elements
+// ahead (the second launch costs more than the load chain it removes: 0.62 vs 0.70, tracer step 0.91 vs 0.97).
 //
 // Bound: HBM. Algorithmic bytes per element*level(*tracer): OP_EULER 256 + (256 + 1408/L)/qsize; OP_DIVERGENCE_WK
 // 384 + 640/L; OP_LAPLACE_* 256 + (640 | 1152)/L.
@@ -463,7 +466,11 @@ cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s
   // several shorter ranges per warp slot balance the tracer step better (A/B: 0.90 / 0.93 / 0.95 / 0.96 of the measured
   // peak at 1 / 2 / 4 / 8 waves, qsize 4; laplace_simple 0.56 / 0.55 / 0.53 / 0.48) — profiles/README.md
   static const int waves_env = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 0; }();
-  const int waves = waves_env > 0 ? waves_env : (OP == OP_EULER ? (a.Q >= 4 ? 6 : 2 * a.Q - 1) : 1);  // qsize 1 -> 1 wave
+  // tracer step: 1 wave at qsize 1, 6 from qsize 4; divergence_sphere_wk: 8 (0.85 / 0.87 / 0.95 / 0.99 at 1 / 2 / 4 / 8);
+  // laplacians: 1 (0.70 / 0.68 / 0.66 / 0.63)
+  const int waves = waves_env > 0 ? waves_env
+                    : OP == OP_EULER ? (a.Q >= 4 ? 6 : 2 * a.Q - 1)
+                    : OP == OP_DIVWK ? 8 : 1;
   long long blocks = (long long)sm_count() * per_sm * waves;
   const long long need = (a.units + WPC - 1) / WPC;
   if (blocks > need) blocks = need;
