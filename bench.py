@@ -320,7 +320,7 @@ def max_pointwise_rel_err(got, want, names):
     return worst, where
 
 
-def link_probe(dev, h2d_bytes, d2h_bytes, total=1 << 29):
+def link_probe(dev, h2d_bytes, d2h_bytes, total=1 << 29, sync=None):
     """What this GPU's host link does right now, in this process (pinned buffers, two streams, best of 4): host->device
     alone, device->host alone, both at once with equal sizes (duplex), and both at once IN THE PROPORTION OF ONE e2e
     STEP (h2d_bytes : d2h_bytes) — the time of that last probe, scaled to the step's bytes, is the link-bound time of a
@@ -340,6 +340,8 @@ def link_probe(dev, h2d_bytes, d2h_bytes, total=1 << 29):
         best = 1e30
         for _ in range(4):
             torch.cuda.synchronize(dev)
+            if sync is not None:
+                sync()                               # every rank runs the SAME probe at the same time
             t0 = time.perf_counter()
             if bi:
                 with torch.cuda.stream(s1):
@@ -541,7 +543,7 @@ def main():
             e2e_wins = sample_windows(E, seed=2000 + rank)
             e2e_states = oracle_states(td, e2e_wins, L)
         barrier()                                    # every rank probes its link at the same time
-        link = link_probe(dev, h2d, d2h)
+        link = link_probe(dev, h2d, d2h, sync=barrier if world > 1 else None)
         h.compute_and_apply_rhs_host(td.arrays, mode, args.e2e_chunk)
         barrier()
         t0 = time.perf_counter()

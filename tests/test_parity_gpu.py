@@ -712,6 +712,54 @@ def test_biharmonic_is_two_laplacians():
     assert rel_err(got, want) <= 2 * TOL
 
 
+def test_level_local_operators_are_linear_at_scale():
+    """Size-independent property at ne=120 / 4 (21600 elements, nlev=72), where no CPU oracle run is affordable for every
+    element: the tracer step and laplace_tensor are linear in the field —
+    op(alpha*x + beta*y) == alpha*op(x) + beta*op(y) to 1e-12 of the maximum — plus an oracle check of the last 8 elements
+    (high element indices: TMA slice coordinates near the end of the arrays)."""
+    orc = harness.PortOracle()
+    E, L, Q = 21600, 72, 2
+    rng = np.random.default_rng(5)
+    s = orc.init(E, L, qsize_d=Q)
+    tail = harness.randomize(orc.init(8, L, qsize_d=Q), seed=3)
+    for n in harness.FIELD_NAMES:                     # random geometry and fields in the last 8 elements
+        s.arrays[n][E - 8:] = tail.arrays[n]
+    x = rng.uniform(0.5, 1.5, size=(E, L, 4, 4))
+    y = rng.uniform(0.5, 1.5, size=(E, L, 4, 4))
+    alpha, beta = 1.75, -0.625
+    vstar = rng.uniform(-40.0, 40.0, size=(E, L, 4, 4, 2))
+    tv = rng.uniform(-1.0, 1.0, size=(E, 4, 4, 2, 2))
+    h = tb.Caar(E, L, Q)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.upload_extra(tb.X_TENSORVISC, tv)
+    h.upload_vstar(vstar)
+
+    def lap(f):
+        h.upload_extra(tb.X_SCALAR_IN, np.ascontiguousarray(f))
+        h.sphere_wk(tb.OP_LAPLACE_TENSOR, tb.MODE_FAST)
+        return h.download_extra(tb.X_SCALAR_OUT, (E, L, 4, 4))
+
+    def step(q0, q1):
+        s.arrays["elem_state_Qdp"][:, 0, 0] = q0
+        s.arrays["elem_state_Qdp"][:, 1, 0] = q1
+        h.upload(s.arrays)
+        h.euler_step(0, Q, 150.0, tb.MODE_FAST)
+        return h.download_qtens()
+
+    lx, ly, lz = lap(x), lap(y), lap(alpha * x + beta * y)
+    assert rel_err(lz, alpha * lx + beta * ly) <= 4 * TOL
+    want = orc.sphere_wk("laplace_tensor", s, x, tv, nets=E - 8, nete=E)
+    assert rel_err(lx[E - 8:], want[E - 8:]) <= TOL
+    qa = step(x, y)
+    qb = step(alpha * x + beta * y, x)
+    assert rel_err(qb[:, 0], alpha * qa[:, 0] + beta * qa[:, 1]) <= 4 * TOL
+    wq = np.zeros((E, Q, L, 4, 4))
+    s.ctl[0:2] = (E - 8, E)
+    orc.euler_step(s, vstar, wq, 0, Q, 150.0)
+    assert rel_err(qb[E - 8:], wq[E - 8:]) <= TOL
+    h.close()
+
+
 def test_zz_report_pointwise_errors(capsys):
     """Not a gate: prints the worst POINTWISE relative error per field over every fast-mode comparison of this session
     (the gate is field-normalised); run last by name."""
