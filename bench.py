@@ -54,12 +54,12 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch(nelem, nlev):
+def ncu_traffic_per_launch(nelem, nlev, eulerian=False):
     """dram bytes per launch of the fused kernel from the committed ncu --set full capture, scaled to this
     launch's element count (traffic is linear in elements); None until a capture exists."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        t = json.load(open(p))["by_nlev"][str(nlev)]
+        t = json.load(open(p))["by_nlev_eulerian" if eulerian else "by_nlev"][str(nlev)]
         return float(t["dram_bytes_per_elem"]) * nelem
     except Exception:
         return None
@@ -376,6 +376,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-target-s", type=float, default=15.0)
+    ap.add_argument("--eulerian", action="store_true",
+                    help="rsplit == 0: the Eulerian vertical coordinate (SURVEY 8f rank 3) instead of the reference's "
+                         "vertically Lagrangian path; hybi = linspace(0,1); the checker is then the CPU restatement")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check after the timed loops")
     ap.add_argument("--no-clock-topup", action="store_true",
                     help="do not continue the kernel loop after a short timed region to collect 5 clock samples (keeps the "
@@ -450,7 +453,13 @@ def main():
     h = tb.Caar(E, L, device=local_rank)
     h.set_params(td.consts, td.dvv, td.ps0, td.hyai)
     h.set_control(*[int(x) for x in td.ctl], dt2=td.dt2)
+    hybi = np.linspace(0.0, 1.0, L + 1)
+    if args.eulerian:
+        h.set_vertical_coordinate(0, hybi)
     h.upload(td.arrays)
+
+    def oracle_run(orc_, st_, calls, threads):
+        return orc_.run_eulerian(st_, hybi, calls, threads) if args.eulerian else orc_.run(st_, calls, threads)
 
     # ---- resident-state throughput: W warm-up steps, then exactly K steps between CUDA events
     h.compute_and_apply_rhs(args.warmup, mode)
@@ -514,12 +523,12 @@ def main():
     parity = None
     if not args.no_parity:
         from oracle import harness
-        orc = harness.best_oracle(L)
+        orc = harness.PortOracle() if args.eulerian else harness.best_oracle(L)   # the reference has no rsplit == 0 branch
         wins = sample_windows(E, seed=1000 + rank)
         states = oracle_states(td, wins, L)          # td still holds the inputs: nothing has written the host arrays
         worst, nchk, pw, pw_field = 0.0, 0, 0.0, None
         for (a, b), st in zip(wins, states):
-            orc.run(st, calls_done, 1)
+            oracle_run(orc, st, calls_done, 1)
             got = h.download_range(a, b, names=harness.MUTATED)
             worst = max(worst, max_rel_err(got, st.arrays, harness.MUTATED))
             e_pw, f_pw = max_pointwise_rel_err(got, st.arrays, harness.MUTATED)
@@ -559,7 +568,7 @@ def main():
             from oracle import harness
             worst = 0.0
             for (a, b), st in zip(e2e_wins, e2e_states):
-                orc.run(st, 1 + args.e2e_steps, 1)
+                oracle_run(orc, st, 1 + args.e2e_steps, 1)
                 worst = max(worst, max_rel_err({n: td.arrays[n][a:b] for n in harness.MUTATED}, st.arrays, harness.MUTATED))
             parity["e2e_max_rel_err"] = worst
             parity["e2e_calls"] = 1 + args.e2e_steps
@@ -617,7 +626,7 @@ def main():
         st.arrays = td.arrays
         st.ctl = np.array([0, E] + [int(x) for x in td.ctl[2:6]], dtype=np.int32)
         st.dt2, st.consts, st.dvv, st.ps0, st.hyai = td.dt2, td.consts, td.dvv, td.ps0, td.hyai
-        orc.run(st, 1, max(1, cpu_threads() // max(1, world)))
+        oracle_run(orc, st, 1, max(1, cpu_threads() // max(1, world)))
         want = np.array(orc.norms(st)) ** 2
         nerr = torch.tensor([float(np.max(np.abs(ss_local - want) / want))], dtype=torch.float64, device=dev)
         if world > 1:
@@ -639,12 +648,13 @@ def main():
 
     # ---- roofline of the dominant (only) kernel of a step
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = b_alg(L) * E * L
+    alg_bytes = (b_alg(L) + (256.0 * (L + 1) / L if args.eulerian else 0.0)) * E * L   # + the eta_dot_dpdn read-modify-write
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_launch(E, L), "peak_source": peak_src,
+                "traffic": ncu_traffic_per_launch(E, L, args.eulerian), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8000": achieved / 8000.0,
-                "kernel": "caar_fused_kernel" if mode == tb.MODE_FAST else "caar_strict_kernel",
+                "kernel": ("caar_fused_kernel" if mode == tb.MODE_FAST else "caar_strict_kernel") +
+                          (" (Eulerian instance, rsplit == 0)" if args.eulerian else ""),
                 "note": "the measured peak is a 50/50 read/write copy; this kernel's traffic is 62 % reads, and the "
                         "library's own saxpby (67 % reads) streams 6.6-6.8 TB/s on the same GPUs (profiles/README.md)"}
 
@@ -669,6 +679,7 @@ def main():
                                    f"{E} elements per GPU ({E_total} in total), np=4, nlev={L}, FP64, "
                                    f"n0/np1/nm1 distinct, qn0=0",
                        "elements_per_gpu": E, "nlev": L, "mode": args.mode, "host_cpus_bound": numa,
+                       "vertical_coordinate": "Eulerian (rsplit == 0)" if args.eulerian else "Lagrangian (the reference's path)",
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed" %
                              (sum(a.nbytes for a in td.arrays.values()) / 1e9)},
             "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,

@@ -454,14 +454,22 @@ cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s
   const unsigned in_b = (OP == OP_DIVWK) ? 2048u : 1024u, item_b = (OP == OP_EULER) ? 2048u : 0u;
   const size_t smem = (size_t)WPC * (NS * in_b + NO * 1024u + 2 * item_b) + WPC * (NS + 2) * sizeof(uint64_t) +
                       WPC * 80 * sizeof(double) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // function attributes and occupancy are per (instance, device): set / queried once
+  static int cached_per_sm[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
-  int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levelop_kernel<OP>, 32 * WPC, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
+  int per_sm = (dev >= 0 && dev < 64) ? cached_per_sm[dev] : 0;
+  if (per_sm == 0) {
+    e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(levelop_kernel<OP>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levelop_kernel<OP>, 32 * WPC, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (dev >= 0 && dev < 64) cached_per_sm[dev] = per_sm;
+  }
   // grid = waves x the resident CTAs: one wave (fully persistent) is best for the shuffle-heavy weak-form operators,
   // several shorter ranges per warp slot balance the tracer step better (A/B: 0.90 / 0.93 / 0.95 / 0.96 of the measured
   // peak at 1 / 2 / 4 / 8 waves, qsize 4; laplace_simple 0.56 / 0.55 / 0.53 / 0.48) — profiles/README.md
