@@ -278,6 +278,11 @@ __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int
 #ifndef CAAR_PARK
 #define CAAR_PARK 1
 #endif
+#ifndef CAAR_EUL_HOIST
+#define CAAR_EUL_HOIST 56  // Eulerian instances with at least this many levels per CTA issue the block's two global loads
+                           // (dp3d re-read, eta_dot_dpdn) at its start: A/B nlev=128 (64 levels per CTA) 0.847 -> 0.861 of
+                           // the measured peak, nlev=72 (24 per CTA) 0.878 -> 0.849 (the 16 live registers cost more there)
+#endif
 #ifndef CAAR_CL72
 #define CAAR_CL72 3   // nlev = 72: the column is split over a cluster of three 96-thread CTAs (24 levels each)
 #endif
@@ -731,7 +736,13 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     // ---- late inputs, second batch (omega_p, T(nm1), v(nm1))
     mbar_wait(&S.bar[1], 0);
     const Row mp = ld_row(S.mp + r * 4);
+    Row eta_old, dpk_early;  // Eulerian: the two global loads of this block, issued before the math that hides their latency
+    constexpr bool HOIST = EUL && (CAAR_EUL_HOIST > 0) && (LC >= CAAR_EUL_HOIST);
     if (EUL) {
+      if (HOIST && live) {
+        dpk_early = ld_row(A.dp3d + on0);
+        if (lev0 + (t >> 2) > 0) eta_old = ld_row(A.eta_dot_dpdn + e * (lf + PTS) + off);
+      }
       // finish what frees registers first (a, rp, ttb, ph, cq die here): omega_p, the T tendency without T_vadv,
       // phi and Ephi
       {
@@ -780,7 +791,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       }
       if (kg > 0 && live) {  // derived_eta_dot_dpdn(k) += eta_ave_w*eta(k) (F:270-277); interfaces 0 and L carry no flux
         double* pe = A.eta_dot_dpdn + e * (lf + PTS) + off;
-        Row x = ld_row(pe);
+        Row x = HOIST ? eta_old : ld_row(pe);
 #pragma unroll
         for (int j = 0; j < 4; ++j) x.x[j] = fma(A.eta_ave_w, elo.x[j], x.x[j]);
         st_row(pe, x);
@@ -789,7 +800,8 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       // forms at the top and bottom follow from eta = 0 there
       {
         Row dpk;  // re-read (L1/L2 hit) rather than 4 doubles live through the scans
-        if (live) dpk = ld_row(A.dp3d + on0);
+        if (HOIST) dpk = dpk_early;
+        else if (live) dpk = ld_row(A.dp3d + on0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const double hr = live ? 0.5 * fast_rcp(dpk.x[j]) : 0.0;
