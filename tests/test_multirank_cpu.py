@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import harness
-from tinman_sandbox_b200.partition import element_range, reduce_norms
+from tinman_sandbox_b200.partition import element_range, reduce_checksums, reduce_norms
 from tinman_sandbox_b200.testdata import TestData
 
 E_TOTAL = 9
@@ -30,6 +30,22 @@ def test_partition_covers_everything_once():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         element_range(2, 2, 10)
+
+
+CS_FIELDS = ("elem_state_dp3d", "elem_state_v", "elem_state_T", "elem_derived_eta_dot_dpdn", "elem_derived_omega_p",
+             "elem_derived_phi", "elem_derived_vn0")
+
+
+def _checksums(arrays, tl):
+    """numpy stand-in for caar_checksums (include/caar_b200.h): sum, sum of squares, bit-pattern sum mod 2^64"""
+    out = {"sum": [], "sumsq": [], "bits": [], "energy": [0.0, 0.0]}
+    for n in CS_FIELDS:
+        a = arrays[n][:, tl] if n.startswith("elem_state") else arrays[n]
+        a = np.ascontiguousarray(a)
+        out["sum"].append(a.sum())
+        out["sumsq"].append((a * a).sum())
+        out["bits"].append(a.view(np.uint64).sum(dtype=np.uint64))
+    return out
 
 
 def _worker(rank, world, port, out_dir):
@@ -53,6 +69,9 @@ def _worker(rank, world, port, out_dir):
 
     norms = reduce_norms(local, allreduce)
     np.save(os.path.join(out_dir, f"norms_{rank}.npy"), norms)
+    cs = reduce_checksums(_checksums(s.arrays, np1), allreduce)       # what caar_checksums returns per rank, from numpy
+    np.save(os.path.join(out_dir, f"bits_{rank}.npy"), cs["bits"])
+    np.save(os.path.join(out_dir, f"sums_{rank}.npy"), np.concatenate([cs["sum"], cs["sumsq"]]))
     np.save(os.path.join(out_dir, f"T_{rank}.npy"), s.arrays["elem_state_T"][:, np1])
     dist.barrier()
     dist.destroy_process_group()
@@ -68,5 +87,12 @@ def test_two_ranks_reproduce_the_single_process_run(tmp_path):
     n0, n1 = np.load(tmp_path / "norms_0.npy"), np.load(tmp_path / "norms_1.npy")
     assert np.array_equal(n0, n1)                                   # every rank holds the reduced result
     assert np.max(np.abs(n0 - want) / want) < 1e-13                 # sum order differs from the Kahan loop
+    # checksums: the 64-bit integer all-reduce of the bit-pattern sums is exact and partition-independent
+    b0, b1 = np.load(tmp_path / "bits_0.npy"), np.load(tmp_path / "bits_1.npy")
+    want_cs = _checksums(full.arrays, 1)
+    assert np.array_equal(b0, b1) and np.array_equal(b0, np.array(want_cs["bits"], dtype=np.uint64))
+    s0 = np.load(tmp_path / "sums_0.npy")
+    want_s = np.array(want_cs["sum"] + want_cs["sumsq"])
+    assert np.max(np.abs(s0 - want_s) / np.maximum(np.abs(want_s), 1e-300)) < 1e-13
     T = np.concatenate([np.load(tmp_path / "T_0.npy"), np.load(tmp_path / "T_1.npy")])
     assert np.array_equal(T, full.arrays["elem_state_T"][:, 1])     # slices == the global run, bit for bit
