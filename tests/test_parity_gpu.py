@@ -648,7 +648,7 @@ def test_set_stream_orders_against_the_previous_stream():
 
 
 @pytest.mark.parametrize("mode", [tb.MODE_STRICT, tb.MODE_FAST])
-@pytest.mark.parametrize("nlev", [72, 128, 30, 26, 100, 5])
+@pytest.mark.parametrize("nlev", [72, 128, 30, 26, 100, 5, 16, 17, 41])
 def test_weak_form_operators(mode, nlev):
     """SURVEY §8f rank 4, the hyperviscosity half: divergence_sphere_wk, laplace_simple, laplace_tensor and
     laplace_tensor_replace (LV/SphereOperators.hpp:493-636) through caar_sphere_wk against the CPU restatement, which is

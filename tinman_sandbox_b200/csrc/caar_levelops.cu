@@ -360,6 +360,263 @@ __global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const _
   if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk stores
 }
 
+// ---- laplace_simple / laplace_tensor, second generation: ONE THREAD PER LEVEL ------------------------------------
+// The row decomposition above spends most of its issue slots and LSU wavefronts on moving the 16 values of a level
+// between its four threads (48 SHFL.32 + 4 LDS/STS.128 per thread and tile, against 80 DFMA). Here a thread owns all 16
+// points of one level: its 128-byte row of the swizzled tile is 8 conflict-free LDS.128, both derivatives and the weak
+// divergence are thread-local (320 DFMA, no shuffle), and the point-local 2x2 matrices N come from a per-warp
+// shared-memory cache read with broadcast LDS.128. The element x level rows of [nets,nete) are ONE flat list (the
+// scalar arrays are [E][L][16] without padding), cut into tiles of 32 rows = 4 KB = one warp step, so every lane is busy
+// whatever nlev is; a tile may span several elements (at most 3 for nlev >= 16), each lane picks the cache slot of its own
+// element; the geometry of new elements is pulled into L2 five tiles ahead, loaded into registers two tiles ahead and
+// turned into N one tile ahead, after the math (loaded on demand, a quarter of all warp stall samples sat on those loads;
+// loaded one tile ahead, still 7 %: under load a line takes longer than a tile's math even from L2). Same per-warp TMA pipeline as above (FN input tiles ahead, FO output tiles draining).
+#ifndef LAPFLAT_NS
+#define LAPFLAT_NS 3
+#endif
+#ifndef LAPFLAT_NO
+#define LAPFLAT_NO 2
+#endif
+#ifndef LAPFLAT_WPC
+#define LAPFLAT_WPC 4
+#endif
+#ifndef LAPFLAT_MINB
+#define LAPFLAT_MINB 2
+#endif
+#ifndef LAPFLAT_PD
+#define LAPFLAT_PD 5  // tiles between the L2 prefetch of an element's geometry and its use
+#endif
+#ifndef LAPFLAT_TPW
+#define LAPFLAT_TPW 16  // tiles per warp the grid size aims at
+#endif
+constexpr int FN = LAPFLAT_NS, FO = LAPFLAT_NO, FW = LAPFLAT_WPC;
+constexpr int FT = 32;            // rows (element x level) per tile
+constexpr unsigned FT_B = 4096u;  // bytes of a tile
+constexpr int FSLOT = 8;          // cached elements per warp (slot = element & 7): <= 3 of this tile + <= 3 of the next
+constexpr unsigned FWARP_B = (FN + FO) * FT_B + FSLOT * 512u;
+
+struct LapFlatArgs {
+  const double* Dinv;
+  const double* spheremp;
+  const double* tensorvisc;
+  int nlev, nets;
+  long long rows;   // (nete - nets) * nlev
+  long long tiles;  // ceil(rows / 32)
+  double rrearth;
+  double dvv[16];
+};
+struct alignas(64) LapFlatMaps {
+  CUtensorMap in, out;  // [1][rows][16 doubles] starting at element nets, box 32 rows
+};
+
+template <bool TENSOR>
+__global__ void __launch_bounds__(32 * FW, LAPFLAT_MINB) laplace_flat_kernel(const __grid_constant__ LapFlatArgs A,
+                                                                             const __grid_constant__ LapFlatMaps M) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* in_tiles = base + w * FWARP_B;
+  unsigned char* out_tiles = in_tiles + FN * FT_B;
+  double* ncache = reinterpret_cast<double*>(out_tiles + FO * FT_B);  // [FSLOT][16 points][4]
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + FW * FWARP_B) + w * FN;
+
+  const long long wid = (long long)blockIdx.x * FW + w, nwarps = (long long)gridDim.x * FW;
+  const long long t0 = A.tiles * wid / nwarps, t1 = A.tiles * (wid + 1) / nwarps;
+  const int n = (int)(t1 - t0);
+  if (n <= 0) return;  // whole warp
+
+  if (lane == 0) {
+    for (int s = 0; s < FN; ++s) mbar_init(&full[s], 1);
+    fence_proxy_async();
+    for (int i = 0; i < FN && i < n; ++i) {
+      mbar_expect_tx(&full[i], FT_B);
+      tma_load(in_tiles + i * FT_B, &M.in, (int)(t0 + i) * FT, 0, &full[i]);
+    }
+  }
+  __syncwarp();
+
+  // (element, level) of the tile's first row, advanced by 32 rows per tile without divisions
+  const int L = A.nlev;
+  int e_first = (int)((t0 * FT) / L), k_first = (int)((t0 * FT) % L);
+  const int e_max = (int)((A.rows - 1) / L);  // last element of the range (relative to nets)
+  int filled = e_first - 1;                   // elements <= filled are (or were) in the cache
+  const uint32_t swz = (uint32_t)lane * 128u;
+  const uint32_t x7 = (uint32_t)(lane & 7);
+
+  // the element's geometry as loaded (lanes 0-15 / 16-31: point lane & 15 of one element each) and its N into the cache
+  struct Geo {
+    double2 a, b, c, d;
+    double mp;
+  };
+  const int pt = lane & 15, half = lane >> 4;
+  auto load_geo = [&](int e) {
+    Geo g;
+    const size_t ge = (size_t)(A.nets + e);
+    g.a = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + pt * 4));
+    g.b = __ldg(reinterpret_cast<const double2*>(A.Dinv + ge * 64 + pt * 4 + 2));
+    g.mp = __ldg(A.spheremp + ge * 16 + pt);
+    if (TENSOR) {
+      g.c = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + pt * 4));
+      g.d = __ldg(reinterpret_cast<const double2*>(A.tensorvisc + ge * 64 + pt * 4 + 2));
+    }
+    return g;
+  };
+  auto store_n = [&](int e, const Geo& g) {  // N = spheremp rrearth^2 Dinv [tensorVisc] Dinv^T (see levelop_kernel)
+    double t00 = g.a.x, t01 = g.b.x, t10 = g.a.y, t11 = g.b.y;
+    if (TENSOR) {
+      const double u00 = fma(g.c.x, t00, g.c.y * t10), u01 = fma(g.c.x, t01, g.c.y * t11);
+      const double u10 = fma(g.d.x, t00, g.d.y * t10), u11 = fma(g.d.x, t01, g.d.y * t11);
+      t00 = u00; t01 = u01; t10 = u10; t11 = u11;
+    }
+    const double sc = g.mp * A.rrearth * A.rrearth;
+    double* dst = ncache + (e & (FSLOT - 1)) * 64 + pt * 4;
+    *reinterpret_cast<double2*>(dst) = make_double2(sc * fma(g.a.x, t00, g.a.y * t10), sc * fma(g.a.x, t01, g.a.y * t11));
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(sc * fma(g.b.x, t00, g.b.y * t10), sc * fma(g.b.x, t01, g.b.y * t11));
+  };
+  auto last_of_tile = [&](int e0, int k0) {  // last element a 32-row tile starting at (e0, k0) touches
+    int k = k0 + FT - 1;
+    while (k >= L) k -= L, ++e0;
+    return e0 < e_max ? e0 : e_max;
+  };
+
+  // Under load a geometry line takes longer from HBM than one tile's math: a second cursor runs FPD tiles ahead and pulls
+  // the lines of the elements it meets into L2 (4 of Dinv, 1 of spheremp, 4 of tensorVisc: lanes 0-8)
+  int e_far = e_first, k_far = k_first, far = e_first - 1;
+  auto far_step = [&]() {
+    const int last = last_of_tile(e_far, k_far);
+    while (far < last) {
+      ++far;
+      const size_t ge = (size_t)(A.nets + far);
+      const double* line = lane < 4 ? A.Dinv + ge * 64 + lane * 16
+                           : lane == 4 ? A.spheremp + ge * 16
+                                       : A.tensorvisc + ge * 64 + (lane - 5) * 16;
+      if (lane < (TENSOR ? 9 : 5)) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+    k_far += FT;
+    while (k_far >= L) k_far -= L, ++e_far;
+  };
+  for (int d = 0; d <= LAPFLAT_PD; ++d) far_step();
+
+  // Two stages of geometry in registers: `gb` (new elements of the next tile: N stored after this tile's math) and `ga`
+  // (new elements of the tile after it, loaded at the top of this iteration), each at most one element per half warp
+  // (nlev >= 16: a 32-row tile brings at most two new elements). `queued` = last element loaded into a stage.
+  Geo ga, gb;
+  int ga_e = 0, gb_e = 0;
+  bool ga_ok = false, gb_ok = false;
+  int queued = filled;
+
+  for (int i = 0; i < n; ++i) {
+    far_step();
+    // this lane's element (relative) and the last element the tile touches
+    int e_t = e_first, kk = k_first + lane;
+    while (kk >= L) kk -= L, ++e_t;
+    if (e_t > e_max) e_t = e_max;  // rows beyond the range: zero-filled input, clipped output
+    const int e_last = last_of_tile(e_first, k_first);
+    // elements of this tile that are not in the cache yet: the warp's first tile only. Uniform over the warp.
+    while (filled < e_last) {
+      const int e = filled + 1 + half;
+      if (e <= e_last) store_n(e, load_geo(e));
+      filled = filled + 2 < e_last ? filled + 2 : e_last;
+      __syncwarp();
+    }
+    if (queued < filled) queued = filled;
+    k_first += FT;
+    while (k_first >= L) k_first -= L, ++e_first;
+    // the slots the stages go to held elements < e_first of this tile (FSLOT = 8 >= 3 + 2 + 2): nobody reads them any more
+    const int last1 = i + 1 < n ? last_of_tile(e_first, k_first) : filled;
+    int last2 = last1;
+    if (i + 2 < n) {
+      int e2 = e_first, k2 = k_first + FT;
+      while (k2 >= L) k2 -= L, ++e2;
+      last2 = last_of_tile(e2, k2);
+    }
+    if (i == 0) {  // nothing was loaded for the second tile yet
+      gb_e = queued + 1 + half;
+      gb_ok = gb_e <= last1;
+      if (gb_ok) gb = load_geo(gb_e);
+      if (queued < last1) queued = last1;
+    }
+    ga_e = queued + 1 + half;
+    ga_ok = ga_e <= last2;
+    if (ga_ok) ga = load_geo(ga_e);
+    if (queued < last2) queued = last2;
+
+    const int s = i % FN;
+    mbar_wait(&full[s], (i / FN) & 1);
+    const unsigned char* tile = in_tiles + s * FT_B + swz;
+    double sv[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double2 v = *reinterpret_cast<const double2*>(tile + (((uint32_t)c ^ x7) << 4));
+      sv[2 * c] = v.x;
+      sv[2 * c + 1] = v.y;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(FO - 1) : "memory");
+    __syncwarp();  // stage s is consumed by every lane; the output tile i % FO is free
+    if (lane == 0 && i + FN < n) {
+      mbar_expect_tx(&full[s], FT_B);
+      tma_load(in_tiles + s * FT_B, &M.in, (int)(t0 + i + FN) * FT, 0, &full[s]);
+    }
+    unsigned char* otile = out_tiles + (i % FO) * FT_B;
+#if defined(LAPFLAT_DIAG_COPY)  // development: the pipeline without the math
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<double2*>(otile + swz + (((uint32_t)c ^ x7) << 4)) = make_double2(sv[2 * c], sv[2 * c + 1] + (double)e_t);
+#else
+    // raw derivatives: g0(i,j) = sum_m Dvv[m][i] s(m,j), g1(i,j) = sum_m Dvv[m][j] s(i,m); then s = N g in place
+    double g0[16], g1[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double x = A.dvv[0 * 4 + a] * sv[0 * 4 + b], y = A.dvv[0 * 4 + b] * sv[a * 4 + 0];
+#pragma unroll
+        for (int m = 1; m < 4; ++m) {
+          x = fma(A.dvv[m * 4 + a], sv[m * 4 + b], x);
+          y = fma(A.dvv[m * 4 + b], sv[a * 4 + m], y);
+        }
+        g0[a * 4 + b] = x;
+        g1[a * 4 + b] = y;
+      }
+    const double* nc = ncache + (e_t & (FSLOT - 1)) * 64;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      const double2 n01 = *reinterpret_cast<const double2*>(nc + p * 4);
+      const double2 n23 = *reinterpret_cast<const double2*>(nc + p * 4 + 2);
+      const double x = g0[p], y = g1[p];
+      g0[p] = fma(n01.x, x, n01.y * y);
+      g1[p] = fma(n23.x, x, n23.y * y);
+    }
+    // weak divergence: out(i,j) = -(sum_m Dvv[i][m] s0(m,j) + sum_m Dvv[j][m] s1(i,m))
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double o[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int a = c >> 1, b = 2 * (c & 1) + h;
+        double acc = A.dvv[a * 4 + 0] * g0[0 * 4 + b];
+#pragma unroll
+        for (int m = 1; m < 4; ++m) acc = fma(A.dvv[a * 4 + m], g0[m * 4 + b], acc);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc = fma(A.dvv[b * 4 + m], g1[a * 4 + m], acc);
+        o[h] = -acc;
+      }
+      *reinterpret_cast<double2*>(otile + swz + (((uint32_t)c ^ x7) << 4)) = make_double2(o[0], o[1]);
+    }
+#endif
+    if (gb_ok) store_n(gb_e, gb);
+    if (filled < last1) filled = last1;
+    gb = ga; gb_e = ga_e; gb_ok = ga_ok;
+    fence_proxy_async();
+    __syncwarp();  // the output tile is complete and visible to the TMA engine; so is the cache to the next tile
+    if (lane == 0) {
+      tma_store(&M.out, (int)(t0 + i) * FT, 0, otile);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk stores
+}
+
 // ---- CAAR_MODE_STRICT: the reference's operation order, one thread per point, 16 levels per CTA ------------------
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
@@ -486,6 +743,39 @@ cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s
   return cudaGetLastError();
 }
 
+template <bool TENSOR>
+cudaError_t launch_lapflat(const LapFlatArgs& a, const LapFlatMaps& m, cudaStream_t s) {
+  const size_t smem = (size_t)FW * FWARP_B + FW * FN * sizeof(uint64_t) + 1024;
+  static int cached_per_sm[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int per_sm = (dev >= 0 && dev < 64) ? cached_per_sm[dev] : 0;
+  if (per_sm == 0) {
+    e = cudaFuncSetAttribute(laplace_flat_kernel<TENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(laplace_flat_kernel<TENSOR>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, laplace_flat_kernel<TENSOR>, 32 * FW, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (dev >= 0 && dev < 64) cached_per_sm[dev] = per_sm;
+  }
+  static const int waves_env = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 0; }();
+  // grid in waves of resident CTAs: a static cut into one range per resident warp leaves the early finishers idle (0.84 of
+  // the measured peak at 1 wave against 0.96 at 6, 49152 x 128), many short CTAs pay their pipeline fill more often:
+  // about LAPFLAT_TPW tiles per warp, at most 8 waves
+  const long long resident_warps = (long long)sm_count() * per_sm * FW;
+  long long w = (a.tiles + resident_warps * LAPFLAT_TPW / 2) / (resident_warps * LAPFLAT_TPW);
+  w = w < 1 ? 1 : w > 8 ? 8 : w;
+  const int waves = waves_env > 0 ? waves_env : (int)w;
+  long long blocks = (long long)sm_count() * per_sm * waves;
+  const long long need = (a.tiles + FW - 1) / FW;
+  if (blocks > need) blocks = need;
+  laplace_flat_kernel<TENSOR><<<(unsigned)blocks, 32 * FW, smem, s>>>(a, m);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 // Level-local operator on elements [nets,nete). op: 0 tracer step (in = Qdp mirror, item = vstar, out = qtens),
@@ -504,6 +794,19 @@ cudaError_t launch_levelop(int op, const KernelArgs& k, const double* in, const 
     const long long rows = (long long)(nete - nets) * k.nlev;
     sphere_wk_strict_kernel<<<(unsigned)((rows + 15) / 16), 256, 0, s>>>(a);
     return cudaGetLastError();
+  }
+  static const bool lap_v1 = [] { const char* v = getenv("CAAR_LAPLACE_V1"); return v && atoi(v) != 0; }();
+  const long long flat_rows = (long long)(nete - nets) * k.nlev;
+  if (op >= 2 && !lap_v1 && k.nlev >= 16 && flat_rows + FT < (1ll << 31)) {  // thread-per-level laplacians
+    LapFlatArgs a;
+    a.Dinv = k.Dinv; a.spheremp = k.spheremp; a.tensorvisc = tensorvisc;
+    a.nlev = k.nlev; a.nets = nets; a.rows = flat_rows; a.tiles = (flat_rows + FT - 1) / FT; a.rrearth = k.rrearth;
+    for (int i = 0; i < 16; ++i) a.dvv[i] = k.dvv[i];
+    LapFlatMaps m;
+    const size_t off = (size_t)nets * k.nlev * 16;
+    if (encode3(&m.in, in + off, 1, (cuuint64_t)flat_rows, FT) | encode3(&m.out, out + off, 1, (cuuint64_t)flat_rows, FT))
+      return cudaErrorInvalidValue;
+    return op == 2 ? launch_lapflat<false>(a, m, s) : launch_lapflat<true>(a, m, s);
   }
   LevelOpArgs a;
   a.Dinv = k.Dinv; a.metdet = k.metdet; a.rmetdet = k.rmetdet; a.spheremp = k.spheremp; a.tensorvisc = tensorvisc;
