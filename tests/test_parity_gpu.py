@@ -690,6 +690,44 @@ def test_weak_form_operators(mode, nlev):
         assert rel_err(got, want) <= TOL
 
 
+def test_laplace_scheduler_over_many_launches():
+    """The thread-per-level laplacians draw their tiles from a global counter that every launch must leave at zero:
+    300 back-to-back launches over changing element ranges (changing tile and chunk counts, queued without
+    synchronisation), each checked against the oracle afterwards, and two launches of the same range bit-identical
+    (the result does not depend on which warp drew which tile)."""
+    orc = harness.PortOracle()
+    E, L = 48, 40
+    s = harness.randomize(orc.init(E, L), seed=11)
+    rng = np.random.default_rng(12)
+    sin = rng.uniform(200.0, 300.0, size=(E, L, 4, 4))
+    tv = rng.uniform(-1.0, 1.0, size=(E, 4, 4, 2, 2))
+    want = {tb.OP_LAPLACE_SIMPLE: orc.sphere_wk("laplace_simple", s, sin),
+            tb.OP_LAPLACE_TENSOR: orc.sphere_wk("laplace_tensor", s, sin, tv)}
+    h = tb.Caar(E, L)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.upload(s.arrays)
+    h.upload_extra(tb.X_SCALAR_IN, sin)
+    h.upload_extra(tb.X_TENSORVISC, tv)
+    for it in range(300):
+        a = int(rng.integers(0, E - 1))
+        b = int(rng.integers(a + 1, E + 1))
+        op = tb.OP_LAPLACE_SIMPLE if it % 2 else tb.OP_LAPLACE_TENSOR
+        if it % 25 == 24:
+            h.upload_extra(tb.X_SCALAR_OUT, np.full((E, L, 4, 4), -7.0))
+            h.sphere_wk(op, tb.MODE_FAST, nets=a, nete=b)
+            got = h.download_extra(tb.X_SCALAR_OUT, (E, L, 4, 4))
+            assert np.all(got[:a] == -7.0) and np.all(got[b:] == -7.0)
+            assert rel_err(got[a:b], want[op][a:b]) <= TOL, (it, a, b)
+        else:
+            h.sphere_wk(op, tb.MODE_FAST, nets=a, nete=b, sync=False)
+    h.sphere_wk(tb.OP_LAPLACE_TENSOR, tb.MODE_FAST)
+    one = h.download_extra(tb.X_SCALAR_OUT, (E, L, 4, 4)).copy()
+    h.sphere_wk(tb.OP_LAPLACE_TENSOR, tb.MODE_FAST)
+    two = h.download_extra(tb.X_SCALAR_OUT, (E, L, 4, 4))
+    h.close()
+    assert np.array_equal(one, two)
+
+
 def test_biharmonic_is_two_laplacians():
     """A property the composition offers at any size: laplace_simple applied twice through the in-place form equals the
     oracle's two applications (the hyperviscosity operator is nabla^4), ne=30-sized."""

@@ -27,8 +27,10 @@
 //   out(r,j) = q(r,j) + sum_m A(m,j) q(m,j) + c(r,j) sum_m Dvv[m][j] w2(r,m) q(r,m),
 //   c(r,j) = -dt rmetdet(r,j) rrearth,  A(m,j) = c(r,j) Dvv[m][r] w1(m,j),  (w1,w2) = metdet Dinv vstar
 //   — no shuffles and no geometry loads inside the tracer loop.
-// The weak-form operators use the fused kernel's row decomposition: sums along jgp thread-local, sums along igp through
-// three xor-shuffles per value. Tried and rejected (profiles/README.md): exchanging the rows through the shared-memory
+// divergence_sphere_wk (and the laplacians for nlev < 16) use the fused kernel's row decomposition: sums along jgp
+// thread-local, sums along igp through three xor-shuffles per value; the laplacians proper run on laplace_flat_kernel
+// below (one thread per level, tiles drawn from a global counter). Tried and rejected for the row-decomposed laplacians
+// (profiles/README.md): exchanging the rows through the shared-memory
 // tile instead of shuffles (80 fewer instructions per tile, two more __syncwarp round trips: 0.66 vs 0.70 for
 // laplace_simple), and computing the per-element coefficients in a pre-pass kernel with a bulk-copy prefetch two elements
 // ahead (the second launch costs more than the load chain it removes: 0.62 vs 0.70, tracer step 0.91 vs 0.97).
@@ -40,6 +42,8 @@
 // bit-identical to the reference's own HOMMEXX code for the weak-form operators): plain point-per-thread kernels below;
 // the tracer step's strict variant stays in caar_euler.cu.
 #include "caar_fused_kernel.cuh"
+
+#include <atomic>
 
 namespace caar {
 namespace {
@@ -383,12 +387,7 @@ __global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const _
 #ifndef LAPFLAT_MINB
 #define LAPFLAT_MINB 2
 #endif
-#ifndef LAPFLAT_PD
-#define LAPFLAT_PD 5  // tiles between the L2 prefetch of an element's geometry and its use
-#endif
-#ifndef LAPFLAT_TPW
-#define LAPFLAT_TPW 16  // tiles per warp the grid size aims at
-#endif
+static_assert(LAPFLAT_NS >= 3, "the geometry stages look two tiles ahead in the ring of tile numbers");
 constexpr int FN = LAPFLAT_NS, FO = LAPFLAT_NO, FW = LAPFLAT_WPC;
 constexpr int FT = 32;            // rows (element x level) per tile
 constexpr unsigned FT_B = 4096u;  // bytes of a tile
@@ -402,6 +401,8 @@ struct LapFlatArgs {
   int nlev, nets;
   long long rows;   // (nete - nets) * nlev
   long long tiles;  // ceil(rows / 32)
+  unsigned* sched;  // [0] next chunk, [1] warps done: both zero before and after a launch
+  int chunk;        // tiles per chunk
   double rrearth;
   double dvv[16];
 };
@@ -420,26 +421,61 @@ __global__ void __launch_bounds__(32 * FW, LAPFLAT_MINB) laplace_flat_kernel(con
   double* ncache = reinterpret_cast<double*>(out_tiles + FO * FT_B);  // [FSLOT][16 points][4]
   uint64_t* full = reinterpret_cast<uint64_t*>(base + FW * FWARP_B) + w * FN;
 
-  const long long wid = (long long)blockIdx.x * FW + w, nwarps = (long long)gridDim.x * FW;
-  const long long t0 = A.tiles * wid / nwarps, t1 = A.tiles * (wid + 1) / nwarps;
-  const int n = (int)(t1 - t0);
-  if (n <= 0) return;  // whole warp
+  int* tq = reinterpret_cast<int*>(base + FW * FWARP_B + FW * FN * sizeof(uint64_t)) + w * FN;  // tile of each stage
+
+  // Work distribution: the tiles are handed out in chunks of A.chunk consecutive tiles from a global counter (a static
+  // cut into one range per warp left the early finishers idle: 0.84 of the measured peak against 0.95-0.98 with many
+  // short CTAs, which in turn pay their pipeline fill each time). Lane 0 draws the NEXT chunk when the current one starts,
+  // so the atomic's latency is never waited for; the stream of tiles feeds the TMA ring FN tiles ahead of the math.
+  const int L = A.nlev, ntiles = (int)A.tiles, C = A.chunk, nchunks = (ntiles + C - 1) / C;
+  const int nwarps = (int)gridDim.x * FW;
+  unsigned pend = 0;
+  if (lane == 0) pend = atomicAdd(A.sched, 1u);
+  int gen = 0, gen_end = 0;
+  bool exhausted = false, first = true;
+  auto next_tile = [&]() -> int {  // uniform over the warp
+    if (gen == gen_end) {
+      if (exhausted) return -1;
+      int c = (int)blockIdx.x * FW + w;  // the first chunk of a warp is its own number: no round trip before the first load
+      if (!first) {
+        c = nwarps + (int)__shfl_sync(FULL, pend, 0);
+        if (lane == 0 && c < nchunks) pend = atomicAdd(A.sched, 1u);
+      }
+      first = false;
+      if (c >= nchunks) {
+        exhausted = true;
+        return -1;
+      }
+      gen = c * C;
+      gen_end = gen + C < ntiles ? gen + C : ntiles;
+    }
+    return gen++;
+  };
 
   if (lane == 0) {
     for (int s = 0; s < FN; ++s) mbar_init(&full[s], 1);
     fence_proxy_async();
-    for (int i = 0; i < FN && i < n; ++i) {
-      mbar_expect_tx(&full[i], FT_B);
-      tma_load(in_tiles + i * FT_B, &M.in, (int)(t0 + i) * FT, 0, &full[i]);
+  }
+  for (int s = 0; s < FN; ++s) {
+    const int t = next_tile();
+    if (lane == 0) {
+      tq[s] = t;
+      if (t >= 0) {
+        mbar_expect_tx(&full[s], FT_B);
+        tma_load(in_tiles + s * FT_B, &M.in, t * FT, 0, &full[s]);
+      }
     }
   }
   __syncwarp();
 
-  // (element, level) of the tile's first row, advanced by 32 rows per tile without divisions
-  const int L = A.nlev;
-  int e_first = (int)((t0 * FT) / L), k_first = (int)((t0 * FT) % L);
+  const double inv_l = 1.0 / (double)L;
+  auto pos_of = [&](int tile, int& e, int& k) {  // (element, level) of a tile's first row; exact: (row + 1/2)/L is at
+    const int row = tile * FT;                   // least 1/(2L) away from an integer
+    e = __double2int_rd(((double)row + 0.5) * inv_l);
+    k = row - e * L;
+  };
   const int e_max = (int)((A.rows - 1) / L);  // last element of the range (relative to nets)
-  int filled = e_first - 1;                   // elements <= filled are (or were) in the cache
+  int filled = -1;                            // elements <= filled are (or were) in the cache
   const uint32_t swz = (uint32_t)lane * 128u;
   const uint32_t x7 = (uint32_t)(lane & 7);
 
@@ -479,69 +515,52 @@ __global__ void __launch_bounds__(32 * FW, LAPFLAT_MINB) laplace_flat_kernel(con
     return e0 < e_max ? e0 : e_max;
   };
 
-  // Under load a geometry line takes longer from HBM than one tile's math: a second cursor runs FPD tiles ahead and pulls
-  // the lines of the elements it meets into L2 (4 of Dinv, 1 of spheremp, 4 of tensorVisc: lanes 0-8)
-  int e_far = e_first, k_far = k_first, far = e_first - 1;
-  auto far_step = [&]() {
-    const int last = last_of_tile(e_far, k_far);
-    while (far < last) {
-      ++far;
-      const size_t ge = (size_t)(A.nets + far);
-      const double* line = lane < 4 ? A.Dinv + ge * 64 + lane * 16
-                           : lane == 4 ? A.spheremp + ge * 16
-                                       : A.tensorvisc + ge * 64 + (lane - 5) * 16;
-      if (lane < (TENSOR ? 9 : 5)) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-    }
-    k_far += FT;
-    while (k_far >= L) k_far -= L, ++e_far;
-  };
-  for (int d = 0; d <= LAPFLAT_PD; ++d) far_step();
-
-  // Two stages of geometry in registers: `gb` (new elements of the next tile: N stored after this tile's math) and `ga`
-  // (new elements of the tile after it, loaded at the top of this iteration), each at most one element per half warp
-  // (nlev >= 16: a 32-row tile brings at most two new elements). `queued` = last element loaded into a stage.
+  // Two stages of geometry in registers, one element per half warp each: `gb` = the first two new elements of the next
+  // tile (N stored after this tile's math), `ga` = those of the tile after it (loaded at the top of this iteration).
+  // `queued` = last element loaded into a stage. What the stages do not cover (the warp's first tile; a third new element
+  // after a jump when nlev < 32) is loaded on demand.
   Geo ga, gb;
-  int ga_e = 0, gb_e = 0;
+  int ga_e = 0, gb_e = 0, gb_hi = -1, ga_hi = -1;
   bool ga_ok = false, gb_ok = false;
-  int queued = filled;
+  int queued = -1;
+  auto stage = [&](int t, Geo& g, int& g_e, int& g_hi, bool& g_ok) {  // new elements of tile t (t < 0: none)
+    g_ok = false;
+    g_hi = -1;
+    if (t < 0) return;
+    int e, k;
+    pos_of(t, e, k);
+    const int last = last_of_tile(e, k);
+    const int lo = queued > e - 1 ? queued : e - 1;
+    g_e = lo + 1 + half;
+    g_ok = g_e <= last;
+    if (g_ok) g = load_geo(g_e);
+    g_hi = lo + 2 < last ? lo + 2 : last;
+    if (queued < g_hi) queued = g_hi;
+  };
 
-  for (int i = 0; i < n; ++i) {
-    far_step();
+  for (int i = 0;; ++i) {
+    const int s = i % FN;
+    const int tile_id = tq[s];
+    if (tile_id < 0) break;  // uniform
+    const int t1 = tq[(i + 1) % FN], t2 = tq[(i + 2) % FN];
+    int e_first, k_first;
+    pos_of(tile_id, e_first, k_first);
     // this lane's element (relative) and the last element the tile touches
     int e_t = e_first, kk = k_first + lane;
     while (kk >= L) kk -= L, ++e_t;
     if (e_t > e_max) e_t = e_max;  // rows beyond the range: zero-filled input, clipped output
     const int e_last = last_of_tile(e_first, k_first);
-    // elements of this tile that are not in the cache yet: the warp's first tile only. Uniform over the warp.
-    while (filled < e_last) {
+    if (filled < e_first - 1) filled = e_first - 1;
+    while (filled < e_last) {  // not staged: on demand. Uniform over the warp.
       const int e = filled + 1 + half;
       if (e <= e_last) store_n(e, load_geo(e));
       filled = filled + 2 < e_last ? filled + 2 : e_last;
       __syncwarp();
     }
     if (queued < filled) queued = filled;
-    k_first += FT;
-    while (k_first >= L) k_first -= L, ++e_first;
-    // the slots the stages go to held elements < e_first of this tile (FSLOT = 8 >= 3 + 2 + 2): nobody reads them any more
-    const int last1 = i + 1 < n ? last_of_tile(e_first, k_first) : filled;
-    int last2 = last1;
-    if (i + 2 < n) {
-      int e2 = e_first, k2 = k_first + FT;
-      while (k2 >= L) k2 -= L, ++e2;
-      last2 = last_of_tile(e2, k2);
-    }
-    if (i == 0) {  // nothing was loaded for the second tile yet
-      gb_e = queued + 1 + half;
-      gb_ok = gb_e <= last1;
-      if (gb_ok) gb = load_geo(gb_e);
-      if (queued < last1) queued = last1;
-    }
-    ga_e = queued + 1 + half;
-    ga_ok = ga_e <= last2;
-    if (ga_ok) ga = load_geo(ga_e);
-    if (queued < last2) queued = last2;
+    if (i == 0) stage(t1, gb, gb_e, gb_hi, gb_ok);  // nothing was loaded for the second tile yet
+    stage(t2, ga, ga_e, ga_hi, ga_ok);
 
-    const int s = i % FN;
     mbar_wait(&full[s], (i / FN) & 1);
     const unsigned char* tile = in_tiles + s * FT_B + swz;
     double sv[16];
@@ -553,9 +572,15 @@ __global__ void __launch_bounds__(32 * FW, LAPFLAT_MINB) laplace_flat_kernel(con
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(FO - 1) : "memory");
     __syncwarp();  // stage s is consumed by every lane; the output tile i % FO is free
-    if (lane == 0 && i + FN < n) {
-      mbar_expect_tx(&full[s], FT_B);
-      tma_load(in_tiles + s * FT_B, &M.in, (int)(t0 + i + FN) * FT, 0, &full[s]);
+    {
+      const int t = next_tile();
+      if (lane == 0) {
+        tq[s] = t;
+        if (t >= 0) {
+          mbar_expect_tx(&full[s], FT_B);
+          tma_load(in_tiles + s * FT_B, &M.in, t * FT, 0, &full[s]);
+        }
+      }
     }
     unsigned char* otile = out_tiles + (i % FO) * FT_B;
 #if defined(LAPFLAT_DIAG_COPY)  // development: the pipeline without the math
@@ -604,17 +629,27 @@ __global__ void __launch_bounds__(32 * FW, LAPFLAT_MINB) laplace_flat_kernel(con
       *reinterpret_cast<double2*>(otile + swz + (((uint32_t)c ^ x7) << 4)) = make_double2(o[0], o[1]);
     }
 #endif
+    __syncwarp();  // after a jump the staged elements may take the cache slots this tile was reading
     if (gb_ok) store_n(gb_e, gb);
-    if (filled < last1) filled = last1;
-    gb = ga; gb_e = ga_e; gb_ok = ga_ok;
+    if (filled < gb_hi) filled = gb_hi;
+    gb = ga; gb_e = ga_e; gb_hi = ga_hi; gb_ok = ga_ok;
     fence_proxy_async();
     __syncwarp();  // the output tile is complete and visible to the TMA engine; so is the cache to the next tile
     if (lane == 0) {
-      tma_store(&M.out, (int)(t0 + i) * FT, 0, otile);
+      tma_store(&M.out, tile_id * FT, 0, otile);
       bulk_commit();
     }
   }
-  if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk stores
+  if (lane == 0) {
+    bulk_wait_read_all();  // shared memory must outlive the last bulk stores
+    // the last warp of the grid to get here leaves the scheduler's counters at zero for the next launch
+    __threadfence();
+    const unsigned done = atomicAdd(A.sched + 1, 1u);
+    if (done == gridDim.x * FW - 1) {
+      A.sched[0] = 0;
+      A.sched[1] = 0;
+    }
+  }
 }
 
 // ---- CAAR_MODE_STRICT: the reference's operation order, one thread per point, 16 levels per CTA ------------------
@@ -727,15 +762,15 @@ cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s
     if (per_sm < 1) per_sm = 1;
     if (dev >= 0 && dev < 64) cached_per_sm[dev] = per_sm;
   }
-  // grid = waves x the resident CTAs: one wave (fully persistent) is best for the shuffle-heavy weak-form operators,
-  // several shorter ranges per warp slot balance the tracer step better (A/B: 0.90 / 0.93 / 0.95 / 0.96 of the measured
-  // peak at 1 / 2 / 4 / 8 waves, qsize 4; laplace_simple 0.56 / 0.55 / 0.53 / 0.48) — profiles/README.md
+  // grid = waves x the resident CTAs. A static cut into one range per resident warp (1 wave) leaves the early finishers
+  // idle, many short CTAs pay their pipeline fill more often; the best number of waves grows with the size (tracer step,
+  // qsize 4: 1-2 at 5400 elements, 6-8 at 21600, 16 at 86400; divergence_sphere_wk: 1 / 8 / 16 — profiles/README.md):
+  // about 48 (tracer step) / 12 (weak-form operators) units per warp and CTA, at most 16 waves
   static const int waves_env = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 0; }();
-  // tracer step: 1 wave at qsize 1, 6 from qsize 4; divergence_sphere_wk: 8 (0.85 / 0.87 / 0.95 / 0.99 at 1 / 2 / 4 / 8);
-  // laplacians: 1 (0.70 / 0.68 / 0.66 / 0.63)
-  const int waves = waves_env > 0 ? waves_env
-                    : OP == OP_EULER ? (a.Q >= 4 ? 6 : 2 * a.Q - 1)
-                    : OP == OP_DIVWK ? 8 : 1;
+  const long long per_wave = (long long)sm_count() * per_sm * WPC * (OP == OP_EULER ? 48 : 12);
+  long long wv = (a.units + per_wave / 2) / per_wave;
+  wv = (wv < 1 || OP == OP_LAP_SIMPLE || OP == OP_LAP_TENSOR) ? 1 : wv > 16 ? 16 : wv;  // row-decomposed laplacians (nlev < 16): 1
+  const int waves = waves_env > 0 ? waves_env : (int)wv;
   long long blocks = (long long)sm_count() * per_sm * waves;
   const long long need = (a.units + WPC - 1) / WPC;
   if (blocks > need) blocks = need;
@@ -743,14 +778,22 @@ cudaError_t launch_op(const LevelOpArgs& a, const LevelOpMaps& m, cudaStream_t s
   return cudaGetLastError();
 }
 
+// the scheduler's counters: a ring of pairs, one pair per launch (zero before and after each launch; launches that could
+// overlap on different streams draw different pairs)
+constexpr int SCHED_SLOTS = 256;
+__device__ unsigned g_lapflat_sched[SCHED_SLOTS][2];
+
 template <bool TENSOR>
-cudaError_t launch_lapflat(const LapFlatArgs& a, const LapFlatMaps& m, cudaStream_t s) {
-  const size_t smem = (size_t)FW * FWARP_B + FW * FN * sizeof(uint64_t) + 1024;
+cudaError_t launch_lapflat(LapFlatArgs a, const LapFlatMaps& m, cudaStream_t s) {
+  const size_t smem = (size_t)FW * FWARP_B + FW * FN * (sizeof(uint64_t) + sizeof(int)) + 1024;
   static int cached_per_sm[64] = {};
+  static unsigned* sched_base[64] = {};
+  static std::atomic<unsigned> seq{0};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  int per_sm = (dev >= 0 && dev < 64) ? cached_per_sm[dev] : 0;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  int per_sm = cached_per_sm[dev];
   if (per_sm == 0) {
     e = cudaFuncSetAttribute(laplace_flat_kernel<TENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -759,17 +802,19 @@ cudaError_t launch_lapflat(const LapFlatArgs& a, const LapFlatMaps& m, cudaStrea
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, laplace_flat_kernel<TENSOR>, 32 * FW, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    if (dev >= 0 && dev < 64) cached_per_sm[dev] = per_sm;
+    void* p = nullptr;
+    e = cudaGetSymbolAddress(&p, g_lapflat_sched);
+    if (e != cudaSuccess) return e;
+    sched_base[dev] = static_cast<unsigned*>(p);
+    cached_per_sm[dev] = per_sm;
   }
-  static const int waves_env = [] { const char* v = getenv("CAAR_LEVELOP_WAVES"); return v ? atoi(v) : 0; }();
-  // grid in waves of resident CTAs: a static cut into one range per resident warp leaves the early finishers idle (0.84 of
-  // the measured peak at 1 wave against 0.96 at 6, 49152 x 128), many short CTAs pay their pipeline fill more often:
-  // about LAPFLAT_TPW tiles per warp, at most 8 waves
+  // one wave of resident CTAs; chunks of 4 consecutive tiles (49152 x 128: 0.81 / 0.98 / 1.01 / 0.99 / 0.95 / 0.90 of the
+  // measured peak with 1 / 2 / 4 / 8 / 16 / 32; one tile per chunk exposes the draw), 2 when a warp sees few tiles
+  static const int chunk_env = [] { const char* v = getenv("CAAR_LAPLACE_CHUNK"); return v ? atoi(v) : 0; }();
   const long long resident_warps = (long long)sm_count() * per_sm * FW;
-  long long w = (a.tiles + resident_warps * LAPFLAT_TPW / 2) / (resident_warps * LAPFLAT_TPW);
-  w = w < 1 ? 1 : w > 8 ? 8 : w;
-  const int waves = waves_env > 0 ? waves_env : (int)w;
-  long long blocks = (long long)sm_count() * per_sm * waves;
+  a.chunk = chunk_env > 0 ? chunk_env : (a.tiles < resident_warps * 16 ? 2 : 4);
+  a.sched = sched_base[dev] + 2 * (seq.fetch_add(1) % SCHED_SLOTS);
+  long long blocks = (long long)sm_count() * per_sm;
   const long long need = (a.tiles + FW - 1) / FW;
   if (blocks > need) blocks = need;
   laplace_flat_kernel<TENSOR><<<(unsigned)blocks, 32 * FW, smem, s>>>(a, m);
