@@ -630,7 +630,17 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
     if (chunk < 296) chunk = 296;
     if (chunk > 4096) chunk = 4096;
   }
-  const int nchunks = (n + chunk - 1) / chunk;
+  // After the last copy-in nothing overlaps the last kernel and copy-out: the tail of the range is cut finer (the last
+  // chunk in halves, three times), which shortens that drain from one chunk's copy-out to an eighth of it
+  const int full = (n + chunk - 1) / chunk;
+  int tail[5] = {ctl->nets + (full - 1) * chunk, ctl->nete, 0, 0, 0}, ntail = 1;  // boundaries of the pieces of the last chunk
+  for (int k = 0; k < 3 && chunk_elems == 0; ++k) {
+    const int a0 = tail[ntail - 1], a1 = tail[ntail];
+    if (a1 - a0 < 2 * 296) break;
+    tail[ntail] = a0 + (a1 - a0) / 2;
+    tail[++ntail] = a1;
+  }
+  const int nchunks = full - 1 + ntail;
   if (h->n_chunk_ev < 2 * nchunks) {
     cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[2 * nchunks];
     if (!ev) return fail(CAAR_ERR_NOMEM, "host allocation failed");
@@ -657,7 +667,8 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
     if (ce != cudaSuccess) what = #expr; \
   }
   for (int c = 0; c < nchunks && ce == cudaSuccess; ++c) {
-    const int e0 = ctl->nets + c * chunk, e1 = (e0 + chunk < ctl->nete) ? e0 + chunk : ctl->nete;
+    const int e0 = c < full - 1 ? ctl->nets + c * chunk : tail[c - (full - 1)];
+    const int e1 = c < full - 1 ? e0 + chunk : tail[c - (full - 1) + 1];
     for (int i = 0; i < ni; ++i) PIPE_TRY(copy_slice(in[i], h->dev[in[i].f], tab[in[i].f], e0, e1, true, h->s_in));
     PIPE_TRY(cudaEventRecord(h->chunk_ev[2 * c], h->s_in));
     PIPE_TRY(cudaStreamWaitEvent(h->stream, h->chunk_ev[2 * c], 0));

@@ -254,8 +254,31 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 // for its own GLL row r. Lane (q = lane/4, r) loads rows q, q+8, ... and the eight partial sums of a row meet in a
 // butterfly over the lane bits 2..4: 2*NWT/8 LDS.128 + 24 SHFL per call instead of up to 2*NWT LDS.128 per thread.
 // Used by every cluster instance (the carry chain of dependent DADDs becomes a 3-step butterfly).
+#ifndef CAAR_WARP_TOTALS_V2
+#define CAAR_WARP_TOTALS_V2 1
+#endif
 template <int NWT>
 __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int hi, int lane, double (&out)[4]) {
+#if CAAR_WARP_TOTALS_V2
+  // Lane c (+16) sums column c of the rows lo, lo+2, ... (lo+1, lo+3, ...): one 256-byte LDS.64 per pair of rows, the two
+  // halves meet in one xor-shuffle and every lane picks the four columns of its GLL row: about NWT + 10 shared-memory
+  // wavefronts per call against 40 for the butterfly below (which is what the LSU-bound Eulerian instances feel).
+  const int c = lane & 15, h = lane >> 4, r = lane & 3;
+  double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < (NWT + 1) / 2; ++k) {  // every row is loaded (no branch between the loads), the range selects
+    const int ww = 2 * k + h;
+    const double x = tot[ww < NWT ? ww : NWT - 1][c];
+    if (ww >= lo && ww < hi) {
+      if (k & 1) acc2 += x;
+      else acc += x;
+    }
+  }
+  acc += acc2;
+  acc += __shfl_xor_sync(FULL, acc, 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = __shfl_sync(FULL, acc, r * 4 + j);
+#else
   const int q = lane >> 2, r = lane & 3;
   double acc[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -273,6 +296,7 @@ __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int
     for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(FULL, acc[j], d);
 #pragma unroll
   for (int j = 0; j < 4; ++j) out[j] = acc[j];
+#endif
 }
 
 #ifndef CAAR_PARK
