@@ -257,6 +257,10 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
 #ifndef CAAR_WARP_TOTALS_V2
 #define CAAR_WARP_TOTALS_V2 1
 #endif
+#ifndef CAAR_WT_BOTH
+#define CAAR_WT_BOTH CAAR_WARP_TOTALS_V2  // Eulerian, columns of at most 96 levels: carry and column total of div(v dp) from one pass
+                                          // (nlev 72 / 96: 0.919 -> 0.932 / 0.930; nlev 128: 0.904 -> 0.899, so not there)
+#endif
 template <int NWT>
 __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int hi, int lane, double (&out)[4]) {
 #if CAAR_WARP_TOTALS_V2
@@ -297,6 +301,36 @@ __device__ __forceinline__ void warp_totals(const double (*tot)[16], int lo, int
 #pragma unroll
   for (int j = 0; j < 4; ++j) out[j] = acc[j];
 #endif
+}
+// The same pass delivering two sums: rows [0, hi) (the carry of this warp) and all NWT rows (the column total that the
+// Eulerian branch needs next): one set of loads instead of two calls.
+template <int NWT>
+__device__ __forceinline__ void warp_totals_both(const double (*tot)[16], int hi, int lane, double (&pre)[4],
+                                                 double (&all)[4]) {
+  const int c = lane & 15, h = lane >> 4, r = lane & 3;
+  double a0 = 0.0, a1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < (NWT + 1) / 2; ++k) {
+    const int ww = 2 * k + h;
+    const double x = tot[ww < NWT ? ww : NWT - 1][c];
+    if (ww < NWT) {
+      if (k & 1) t1 += x;
+      else t0 += x;
+      if (ww < hi) {
+        if (k & 1) a1 += x;
+        else a0 += x;
+      }
+    }
+  }
+  a0 += a1;
+  t0 += t1;
+  a0 += __shfl_xor_sync(FULL, a0, 16);
+  t0 += __shfl_xor_sync(FULL, t0, 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pre[j] = __shfl_sync(FULL, a0, r * 4 + j);
+    all[j] = __shfl_sync(FULL, t0, r * 4 + j);
+  }
 }
 
 #ifndef CAAR_PARK
@@ -738,9 +772,11 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       bulk_commit();
     }
     double cq[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
+    double S4[4] = {0, 0, 0, 0};  // Eulerian: column total of div(v dp)
     if constexpr (LANE_CARRY) {
       warp_totals<NWT>(S.tot[1], gw + 1, NWT, lane, cq);
-      warp_totals<NWT>(S.tot[2], 0, gw, lane, cd);
+      if constexpr (EUL && CAAR_WT_BOTH && NWT <= 12) warp_totals_both<NWT>(S.tot[2], gw, lane, cd, S4);
+      else warp_totals<NWT>(S.tot[2], 0, gw, lane, cd);
     } else {
 #pragma unroll
       for (int ww = 0; ww < NWT; ++ww) {
@@ -787,9 +823,8 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
       st_tile(S.pec, sw1, ph);
       // column total S of div(v dp) and the vertical mass flux at this level's two interfaces
       // (F/routine_extracted.F90:233-254): eta(k+1) = hybi(k+1)*S - sum_{l<=k} divdp_l, 0 at the top and bottom
-      double S4[4] = {0, 0, 0, 0};
       if constexpr (LANE_CARRY) {
-        warp_totals<NWT>(S.tot[2], 0, NWT, lane, S4);
+        if constexpr (!(CAAR_WT_BOTH && NWT <= 12)) warp_totals<NWT>(S.tot[2], 0, NWT, lane, S4);
       } else {
 #pragma unroll
         for (int ww = 0; ww < NWT; ++ww) {
