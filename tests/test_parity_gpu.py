@@ -690,6 +690,28 @@ def test_weak_form_operators(mode, nlev):
         assert rel_err(got, want) <= TOL
 
 
+@pytest.mark.parametrize("E,nlev", [(1, 16), (1, 20), (2, 33), (3, 128)])
+def test_laplace_fewer_rows_than_a_tile(E, nlev):
+    """Ranges smaller than (or barely larger than) one 32-row tile of the thread-per-level laplacians: the tile is
+    zero-filled past the range on load and clipped on store."""
+    orc = harness.PortOracle()
+    s = harness.randomize(orc.init(E, nlev), seed=E * 100 + nlev)
+    rng = np.random.default_rng(E + nlev)
+    sin = rng.uniform(200.0, 300.0, size=(E, nlev, 4, 4))
+    tv = rng.uniform(-1.0, 1.0, size=(E, 4, 4, 2, 2))
+    h = tb.Caar(E, nlev)
+    h.set_params(s.consts, s.dvv, s.ps0, s.hyai)
+    h.upload(s.arrays)
+    h.upload_extra(tb.X_SCALAR_IN, sin)
+    h.upload_extra(tb.X_TENSORVISC, tv)
+    for op, name in ((tb.OP_LAPLACE_SIMPLE, "laplace_simple"), (tb.OP_LAPLACE_TENSOR, "laplace_tensor")):
+        h.sphere_wk(op, tb.MODE_FAST)
+        got = h.download_extra(tb.X_SCALAR_OUT, (E, nlev, 4, 4))
+        want = orc.sphere_wk(name, s, sin, tv if name == "laplace_tensor" else None)
+        assert rel_err(got, want) <= TOL, name
+    h.close()
+
+
 def test_laplace_scheduler_over_many_launches():
     """The thread-per-level laplacians draw their tiles from a global counter that every launch must leave at zero:
     300 back-to-back launches over changing element ranges (changing tile and chunk counts, queued without
