@@ -69,7 +69,7 @@ struct caar_handle_s {
   long long launches;
   caar::TmaMaps* tma;  // TMA descriptors of the device mirrors (nlev with a TMA-pipelined kernel only)
   // caar_run_host pipeline: copy-in and copy-out streams, two events per element chunk (grown on demand)
-  cudaStream_t s_in, s_out;
+  cudaStream_t s_in, s_in2, s_out;  // s_in2: second copy-in stream (CAAR_HOST_IN_STREAMS=2)
   cudaEvent_t* chunk_ev;
   int n_chunk_ev;
   cudaEvent_t ev_fence;
@@ -207,6 +207,7 @@ int caar_create(caar_handle* out, const caar_dims* dims, int device) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fence, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
   for (int f = 0; f < CAAR_NUM_FIELDS && e == cudaSuccess; ++f) {
     const size_t bytes = field_count(*dims, f) * sizeof(double);
@@ -262,6 +263,7 @@ int caar_destroy(caar_handle h) {
   for (int i = 0; i < h->n_chunk_ev; ++i) cudaEventDestroy(h->chunk_ev[i]);
   delete[] h->chunk_ev;
   if (h->s_in) cudaStreamSynchronize(h->s_in), cudaStreamDestroy(h->s_in);
+  if (h->s_in2) cudaStreamSynchronize(h->s_in2), cudaStreamDestroy(h->s_in2);
   if (h->s_out) cudaStreamSynchronize(h->s_out), cudaStreamDestroy(h->s_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h->tma;
@@ -641,13 +643,13 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
     tail[++ntail] = a1;
   }
   const int nchunks = full - 1 + ntail;
-  if (h->n_chunk_ev < 2 * nchunks) {
-    cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[2 * nchunks];
+  if (h->n_chunk_ev < 3 * nchunks) {
+    cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[3 * nchunks];
     if (!ev) return fail(CAAR_ERR_NOMEM, "host allocation failed");
     for (int i = 0; i < h->n_chunk_ev; ++i) ev[i] = h->chunk_ev[i];
     delete[] h->chunk_ev;
     h->chunk_ev = ev;
-    while (h->n_chunk_ev < 2 * nchunks) {
+    while (h->n_chunk_ev < 3 * nchunks) {
       CU_TRY(cudaEventCreateWithFlags(&h->chunk_ev[h->n_chunk_ev], cudaEventDisableTiming));
       ++h->n_chunk_ev;
     }
@@ -655,6 +657,9 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
   // the copy-in stream must not overtake work already queued on the compute stream (it rewrites the mirrors)
   CU_TRY(cudaEventRecord(h->ev_fence, h->stream));
   CU_TRY(cudaStreamWaitEvent(h->s_in, h->ev_fence, 0));
+  // the copy-in of a chunk may be dealt over two streams (two copy engines reading the host at once)
+  static const int in_streams = [] { const char* e = getenv("CAAR_HOST_IN_STREAMS"); return e ? atoi(e) : 1; }();
+  if (in_streams > 1) CU_TRY(cudaStreamWaitEvent(h->s_in2, h->ev_fence, 0));
   caar::KernelArgs a = make_args(h, ctl);
   // On any failure inside the pipeline the three streams are drained before returning, so that no DMA is still
   // reading or writing the caller's arrays when the caller sees the error (the host arrays may then hold the results
@@ -669,9 +674,14 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
   for (int c = 0; c < nchunks && ce == cudaSuccess; ++c) {
     const int e0 = c < full - 1 ? ctl->nets + c * chunk : tail[c - (full - 1)];
     const int e1 = c < full - 1 ? e0 + chunk : tail[c - (full - 1) + 1];
-    for (int i = 0; i < ni; ++i) PIPE_TRY(copy_slice(in[i], h->dev[in[i].f], tab[in[i].f], e0, e1, true, h->s_in));
+    for (int i = 0; i < ni; ++i)
+      PIPE_TRY(copy_slice(in[i], h->dev[in[i].f], tab[in[i].f], e0, e1, true, (in_streams > 1 && (i & 1)) ? h->s_in2 : h->s_in));
     PIPE_TRY(cudaEventRecord(h->chunk_ev[2 * c], h->s_in));
     PIPE_TRY(cudaStreamWaitEvent(h->stream, h->chunk_ev[2 * c], 0));
+    if (in_streams > 1) {
+      PIPE_TRY(cudaEventRecord(h->chunk_ev[2 * nchunks + c], h->s_in2));
+      PIPE_TRY(cudaStreamWaitEvent(h->stream, h->chunk_ev[2 * nchunks + c], 0));
+    }
     a.nets = e0;
     a.nete = e1;
     PIPE_TRY(fast ? caar::launch_fused(a, h->stream) : caar::launch_strict(a, h->stream));
@@ -683,6 +693,7 @@ int caar_run_host(caar_handle h, const caar_arrays* host, const caar_control* ct
 #undef PIPE_TRY
   if (ce != cudaSuccess) {
     cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->s_in2);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->s_out);
     cudaGetLastError();
