@@ -372,9 +372,10 @@ __global__ void __launch_bounds__(32 * WPC, LEVELOP_MINB) levelop_kernel(const _
 // shared-memory cache read with broadcast LDS.128. The element x level rows of [nets,nete) are ONE flat list (the
 // scalar arrays are [E][L][16] without padding), cut into tiles of 32 rows = 4 KB = one warp step, so every lane is busy
 // whatever nlev is; a tile may span several elements (at most 3 for nlev >= 16), each lane picks the cache slot of its own
-// element; the geometry of new elements is pulled into L2 five tiles ahead, loaded into registers two tiles ahead and
-// turned into N one tile ahead, after the math (loaded on demand, a quarter of all warp stall samples sat on those loads;
-// loaded one tile ahead, still 7 %: under load a line takes longer than a tile's math even from L2). Same per-warp TMA pipeline as above (FN input tiles ahead, FO output tiles draining).
+// element. The geometry of new elements is loaded into registers two tiles ahead and turned into N one tile ahead, after
+// the math (loaded on demand, a quarter of all warp stall samples sat on those loads; one tile ahead, still 7 %: under
+// load a line takes longer than a tile's math). Same per-warp TMA pipeline as above (FN input tiles ahead, FO output
+// tiles draining); the tiles themselves are drawn in chunks from a global counter (see the kernel).
 #ifndef LAPFLAT_NS
 #define LAPFLAT_NS 3
 #endif
