@@ -34,6 +34,11 @@ def main():
     ap.add_argument("--chunk", type=int, nargs="*", default=[0])
     ap.add_argument("--eulerian", action="store_true", help="rsplit == 0 branch")
     ap.add_argument("--random", action="store_true", help="random geometry/fields instead of the closed form")
+    ap.add_argument("--variants", nargs="*", default=None, choices=["distinct", "aliased", "dry", "aliased_dry"],
+                    help="time the same resident state under several controls, one JSON line each: distinct = n0/np1/nm1 "
+                         "= 0/1/2, qn0 = 0 (21 compulsory level-fields); aliased = n0 = np1 = nm1 = 0 (forward Euler / RK "
+                         "stage, F/routine_extracted.F90:6-16: the aliased level is read once, 17); dry = qn0 = -1 (no Qdp "
+                         "read, 20). spheremp = 1 and dt2 = 1e-9 keep the state finite over the repeated in-place calls")
     args = ap.parse_args()
 
     from tinman_sandbox_b200 import capi
@@ -60,28 +65,39 @@ def main():
             td.arrays[n] *= rng.uniform(0.9, 1.1, size=td.arrays[n].shape)
     h = tb.Caar(E, L)
     h.set_params(td.consts, td.dvv, td.ps0, td.hyai)
-    h.set_control(*[int(x) for x in td.ctl], dt2=td.dt2)
+    dt2 = td.dt2
+    if args.variants:
+        dt2 = 1e-9
+        td.arrays["elem_spheremp"][...] = 1.0
+    h.set_control(*[int(x) for x in td.ctl], dt2=dt2)
     if args.eulerian:
         h.set_vertical_coordinate(0, np.linspace(0.0, 1.0, L + 1))
     h.upload(td.arrays)
-    h.compute_and_apply_rhs(args.warmup, mode)
-    best = 1e30
-    for _ in range(args.repeat):
-        h.timer_start()
-        h.compute_and_apply_rhs(args.steps, mode, sync=False)
-        best = min(best, h.timer_stop() / args.steps)
     peak = 6545.6
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    balg = 21 * 128.0 + 1664.0 / L + (256.0 * (L + 1) / L if args.eulerian else 0.0)
-    rate = E * L / (best * 1e-3)
-    out = {"tag": args.tag, "lib": args.lib or "default", "nelem": E, "nlev": L, "mode": args.mode,
-           "ms_per_step": round(best, 4), "Mupdates_per_s": round(rate / 1e6, 1),
-           "GBps": round(rate * balg / 1e9, 1), "frac_measured": round(rate * balg / 1e9 / peak, 4),
-           "env": {k: v for k, v in os.environ.items() if k.startswith("CAAR_")}}
-    print(json.dumps(out), flush=True)
+    for variant in (args.variants or ["distinct"]):
+        aliased, dry = variant.startswith("aliased"), variant.endswith("dry")
+        if args.variants:
+            h.set_control(n0=0, np1=0 if aliased else 1, nm1=0 if aliased else 2, qn0=-1 if dry else 0)
+        h.compute_and_apply_rhs(args.warmup, mode)
+        best = 1e30
+        for _ in range(args.repeat):
+            h.timer_start()
+            h.compute_and_apply_rhs(args.steps, mode, sync=False)
+            best = min(best, h.timer_stop() / args.steps)
+        # compulsory level-fields: 13 read + 8 written; an aliased nm1 = n0 is read once (-4), dry reads no Qdp (-1)
+        fields = 21 - (4 if aliased else 0) - (1 if dry else 0)
+        balg = fields * 128.0 + 1664.0 / L + (256.0 * (L + 1) / L if args.eulerian else 0.0)
+        rate = E * L / (best * 1e-3)
+        out = {"tag": args.tag, "lib": args.lib or "default", "nelem": E, "nlev": L, "mode": args.mode,
+               "variant": variant, "eulerian": bool(args.eulerian), "B_alg": round(balg, 1),
+               "ms_per_step": round(best, 4), "Mupdates_per_s": round(rate / 1e6, 1),
+               "GBps": round(rate * balg / 1e9, 1), "frac_measured": round(rate * balg / 1e9 / peak, 4),
+               "env": {k: v for k, v in os.environ.items() if k.startswith("CAAR_")}}
+        print(json.dumps(out), flush=True)
     if args.host_steps > 0:
         h2d, d2h = h.host_traffic(mode)
         for chunk in args.chunk:
