@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--chunk", type=int, nargs="*", default=[0])
     ap.add_argument("--eulerian", action="store_true", help="rsplit == 0 branch")
     ap.add_argument("--random", action="store_true", help="random geometry/fields instead of the closed form")
-    ap.add_argument("--variants", nargs="*", default=None, choices=["distinct", "aliased", "dry", "aliased_dry"],
+    ap.add_argument("--variants", nargs="*", default=None, choices=["distinct", "aliased", "dry", "aliased_dry"],  # may repeat
                     help="time the same resident state under several controls, one JSON line each: distinct = n0/np1/nm1 "
                          "= 0/1/2, qn0 = 0 (21 compulsory level-fields); aliased = n0 = np1 = nm1 = 0 (forward Euler / RK "
                          "stage, F/routine_extracted.F90:6-16: the aliased level is read once, 17); dry = qn0 = -1 (no Qdp "
@@ -78,6 +78,16 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
+    def sm_clock():  # SM clock and throttle reasons right after a timed loop (NVML); None without pynvml
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            d = pynvml.nvmlDeviceGetHandleByIndex(0)
+            return {"sm_mhz": pynvml.nvmlDeviceGetClockInfo(d, pynvml.NVML_CLOCK_SM),
+                    "reasons": hex(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(d))}
+        except Exception:
+            return None
+
     for variant in (args.variants or ["distinct"]):
         aliased, dry = variant.startswith("aliased"), variant.endswith("dry")
         if args.variants:
@@ -88,6 +98,7 @@ def main():
             h.timer_start()
             h.compute_and_apply_rhs(args.steps, mode, sync=False)
             best = min(best, h.timer_stop() / args.steps)
+        clk = sm_clock()
         # compulsory level-fields: 13 read + 8 written; an aliased nm1 = n0 is read once (-4), dry reads no Qdp (-1)
         fields = 21 - (4 if aliased else 0) - (1 if dry else 0)
         balg = fields * 128.0 + 1664.0 / L + (256.0 * (L + 1) / L if args.eulerian else 0.0)
@@ -96,7 +107,7 @@ def main():
                "variant": variant, "eulerian": bool(args.eulerian), "B_alg": round(balg, 1),
                "ms_per_step": round(best, 4), "Mupdates_per_s": round(rate / 1e6, 1),
                "GBps": round(rate * balg / 1e9, 1), "frac_measured": round(rate * balg / 1e9 / peak, 4),
-               "env": {k: v for k, v in os.environ.items() if k.startswith("CAAR_")}}
+               "clock_after": clk, "env": {k: v for k, v in os.environ.items() if k.startswith("CAAR_")}}
         print(json.dumps(out), flush=True)
     if args.host_steps > 0:
         h2d, d2h = h.host_traffic(mode)
