@@ -199,6 +199,40 @@ __device__ __forceinline__ Row deriv_i(const Row& s, const double (&cx)[4]) {
   }
   return o;
 }
+// The same derivative on the FP64 tensor core (CAAR_DERIV_MMA): for a fixed jgp j the eight levels of a warp form ONE
+// 8x8x4 product D_j = A B_j with A[i'][m] = Dvv[m][i' & 3] (rows 4-7 repeat rows 0-3) and B_j[m][n] = s of level n at
+// (igp m, jgp j). In the mma.m8n8k4 fragment layout the thread lane = 4*level + igp holds exactly B_j[lane & 3][lane >> 2]
+// = its own x[j], and one constant element of A. The result lands transposed: thread (q = lane >> 2, c = lane & 3) holds
+// D_j[q][2c], D_j[q][2c+1] = the derivative at igp q & 3 of the levels 2c and 2c+1. Since the rows q and q + 4 are
+// copies, the lanes with q < 4 hand out their even level and the lanes with q >= 4 their odd one, and every thread
+// fetches its value with ONE 64-bit shuffle: 4 DMMA + 8 SHFL per call instead of 16 DFMA + 24 SHFL — a third of the
+// shared-memory-pipe wavefronts of the derivative (the L1 data pipe is this kernel's co-limiter).
+struct DerivMma {
+  double a;   // A[lane >> 2][lane & 3] = Dvv[lane & 3][(lane >> 2) & 3]
+  int src;    // lane that holds this thread's result
+  bool odd;   // this lane hands out D[.][2c+1] (q >= 4), else D[.][2c]
+};
+__device__ __forceinline__ DerivMma deriv_mma_setup(const double* __restrict__ dvv, int lane) {
+  DerivMma d;
+  const int q = lane >> 2, c = lane & 3;
+  d.a = dvv[c * 4 + (q & 3)];
+  d.odd = q >= 4;
+  // this thread = (level q, igp c): its row of D is c (level even) or c + 4 (level odd), its column pair is q >> 1
+  d.src = ((((q & 1) ? c + 4 : c)) << 2) | (q >> 1);
+  return d;
+}
+__device__ __forceinline__ Row deriv_i(const Row& s, const DerivMma& m) {
+  Row o;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double d0, d1;
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(m.a), "d"(s.x[j]), "d"(0.0), "d"(0.0));
+    o.x[j] = __shfl_sync(FULL, m.odd ? d1 : d0, m.src);
+  }
+  return o;
+}
 // out[l] = sum_m Dvv[m][l] * s[m] (thread-local; Dvv from the constant bank)
 __device__ __forceinline__ Row deriv_j(const Row& s, const double* __restrict__ dvv) {
   Row o;
@@ -214,7 +248,8 @@ __device__ __forceinline__ Row deriv_j(const Row& s, const double* __restrict__ 
 
 // gradient_sphere (PO/sphere_operators.cpp:9-48) for this thread's row; di = this row's Dinv*rrearth in smem,
 // [jgp][2*a+b]
-__device__ __forceinline__ void gradient(const Row& s, const double* di, const double (&cx)[4],
+template <class CX>
+__device__ __forceinline__ void gradient(const Row& s, const double* di, const CX& cx,
                                          const double* __restrict__ dvv, Row& g0, Row& g1) {
   const Row a = deriv_i(s, cx);   // v1[igp][jgp]
   const Row b = deriv_j(s, dvv);  // v2[igp][jgp]
@@ -244,6 +279,12 @@ __device__ __forceinline__ double scan_up(double v, int lane) {  // towards smal
   return v;
 }
 
+#ifndef CAAR_DERIV_MMA
+// 1 = igp derivatives of the fused kernel as DMMA.8x8x4 + one shuffle per value, 0 = 16 DFMA + 24 SHFL per call. A/B on one
+// box (profiles/r2u_mma_ab.jsonl): nlev 72 1.055 -> 1.065 of the measured peak at full clocks and 0.935 -> 1.014 on a
+// power-capped GPU (~1.6 GHz), aliased time levels 0.88 -> 0.91-0.98, Eulerian nlev 72 / 128 0.931 -> 0.984 / 0.904 -> 0.952
+#define CAAR_DERIV_MMA 1
+#endif
 #ifndef CAAR_EUL_REGS
 // register cap of the single-CTA (CL = 1) Eulerian nlev=72 instance. Its live set (dsave, dp, vtens, ttens through the scans) does not
 // fit 96 registers: measured 0.46 of the HBM peak at 96 (2 CTAs/SM, 480 B of spills), 0.55 at 128, 0.61 at 168
@@ -538,6 +579,9 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     }
   }
 
+#if CAAR_DERIV_MMA
+  const DerivMma cx = deriv_mma_setup(A.dvv, lane);  // igp derivatives on the FP64 tensor core (see deriv_i)
+#else
   double cx[4];  // cx[x] = Dvv[r^x][r]; static indices + selects keep Dvv in the constant bank
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
@@ -547,6 +591,7 @@ caar_fused_kernel(const __grid_constant__ KernelArgs A, const __grid_constant__ 
     if (r == 3) c = A.dvv[(3 ^ x) * 4 + 3];
     cx[x] = c;
   }
+#endif
 
   // ---- A: p = hyai0*ps0 + sum_{l<k} dp_l + dp_k/2   (PO:76-97)
   Row rp;
