@@ -59,3 +59,26 @@ def test_product_does_not_touch_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
                     txt = open(os.path.join(dp, f)).read()
                     assert "oracle/" not in txt and "from oracle" not in txt and "import oracle" not in txt, (dp, f)
+
+
+def test_library_is_built_for_sm_100a_with_tma_clusters_and_dmma():
+    """The built library is what DESIGN.md says it is: sm_100a SASS only, the fused kernel instances move their tiles with
+    TMA tensor copies (UTMALDG / UTMASTG), prefetch into L2 (UBLKPF), exchange scan totals between the CTAs of a cluster
+    with st.async (STAS) and differentiate along igp on the FP64 tensor core (DMMA) — tools/sass_census.py, the table in
+    profiles/r2v_sass_census.txt. A build that silently lost one of these (a flag, an #if) fails here, on the CPU."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_census
+    arch, per = sass_census.census(tb.lib_path())
+    assert arch == ["sm_100a"], arch
+    fused = per["caar_fused_kernel"]
+    assert fused["functions"] == 28                      # 14 level counts x {Lagrangian, Eulerian}
+    for op in ("UTMALDG", "UTMASTG", "UBLKPF", "STAS", "SYNCS", "DMMA"):
+        assert fused[op] > 0, op
+    assert fused["DMMA"] >= 20 * fused["functions"]      # 5 igp derivatives x 4 columns per instance
+    for fam in ("levelop_kernel", "laplace_flat_kernel"):
+        assert per[fam]["UTMALDG"] > 0 and per[fam]["UTMASTG"] > 0, fam
+    assert per["caar_strict_kernel"]["DMMA"] == 0        # the bit-exact anchor stays on plain FP64 arithmetic

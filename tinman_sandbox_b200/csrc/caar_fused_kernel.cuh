@@ -1,4 +1,5 @@
-// caar_fused_kernel.cuh — CAAR_MODE_FAST for nlev = 72 / 128: the whole of compute_and_apply_rhs for one element in
+// caar_fused_kernel.cuh — CAAR_MODE_FAST for every nlev <= 128 (an instance compiled for L levels serves any nlev <= L;
+// the examples below are nlev = 72 / 128): the whole of compute_and_apply_rhs for one element in
 // ONE kernel and one HBM pass (every input read once, every output written once; all 18 reference
 // temporaries of PO/compute_and_apply_rhs.cpp:18-35 live in registers).
 //
@@ -11,19 +12,21 @@
 // Data movement (per CTA):
 //   * "early" inputs dp3d(n0), v(n0) — needed at once — are LDG.128'd straight into registers;
 //   * T(n0), Qdp and the "late" inputs derived_vn0, pecnd, derived_omega_p, dp3d(nm1), T(nm1), v(nm1) are fetched by
-//     ONE thread at kernel entry with eight 2-D tiled TMA copies (cp.async.bulk.tensor.2d, SASS UTMALDG.2D, 128-byte
+//     ONE thread at kernel entry with eight 3-D tiled TMA copies (cp.async.bulk.tensor.3d, SASS UTMALDG.3D, 128-byte
 //     swizzle) into shared memory and complete on three mbarriers while the CTA computes: no registers, no LSU, full
 //     prefetch distance;
 //   * every output is written IN PLACE over the late input that has the same shape
 //     (vn0->vn0, pecnd->phi, omega_p->omega_p, dp3d(nm1)->dp3d(np1), T(nm1)->T(np1), v(nm1)->v(np1)) and
-//     leaves the SM as six TMA tile stores (UTMASTG.2D): fully coalesced, asynchronous, no per-thread STG;
+//     leaves the SM as six TMA tile stores (UTMASTG.3D): fully coalesced, asynchronous, no per-thread STG;
 //   * the element's 2-D geometry (Dinv*rrearth, D, metdet, rmetdet, fcor, spheremp, phis: 1664 B) sits in
 //     shared memory and is re-read (warp-broadcast) where used, instead of pinning 40 registers;
 //   * thread 0 prefetches the early inputs and the geometry of a later element into L2 (cp.async.bulk.prefetch.L2).
 //
 // Math:
 //   * sphere operators (PO/sphere_operators.cpp:9-129): derivative along jgp is thread-local (Dvv from the
-//     constant bank), derivative along igp takes the other three rows of the level from lanes lane^1,2,3.
+//     constant bank); derivative along igp: one DMMA.8x8x4 per jgp column differentiates all 8 levels of the warp at
+//     once and one 64-bit shuffle per value brings the (transposed) result home — see deriv_i(const Row&, const
+//     DerivMma&). (-DCAAR_DERIV_MMA=0: the other three rows of the level from lanes lane^1,2,3 and 16 DFMA.)
 //   * vertical integrals (PO:76-97, 280-312, 314-352) in scan form: warp-shuffle scans over the 8 levels of
 //     a warp (lane stride 4); the per-warp totals are combined over the nlev/8 warps of the column — inside a CTA
 //     through shared memory, between the CTAs of the cluster through distributed shared memory: a warp sends its
